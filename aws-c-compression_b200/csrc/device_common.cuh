@@ -1,0 +1,130 @@
+// Shared device-side definitions for the batched Huffman codec (sm_100a).
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace hb {
+
+// Error values written to per-item status arrays (match aws-c-common / compression.h).
+constexpr int32_t kStatusOk = 0;
+constexpr int32_t kStatusShortBuffer = 4;       // AWS_ERROR_SHORT_BUFFER
+constexpr int32_t kStatusUnknownSymbol = 3072;  // AWS_ERROR_COMPRESSION_UNKNOWN_SYMBOL
+
+constexpr uint64_t kNoCap = ~0ull;  // "all the room it needs" (packed layout)
+
+// Decode LUT entry layout: see host/huffman_lut.h.
+constexpr uint32_t kLutLeafFlag = 0x80000000u;
+
+// Device-resident tables of one context. Pointers are device pointers.
+struct DeviceTables {
+    const uint2 *enc;          // [256] {x = pattern (masked to num_bits), y = num_bits}
+    const uint32_t *lut;       // multi-level decode LUT, `lut_count` entries
+    uint32_t lut_count;
+    uint32_t lut_root_bits;
+    uint32_t min_len;          // shortest code length (>= 1 when the table is not empty)
+    uint32_t max_len;
+    uint32_t has_unknown;      // some symbol has no code
+    uint32_t eos_padding;
+};
+
+// Per-call view of an aws_huffman_batch (device pointers), shared by encode and decode kernels.
+struct BatchView {
+    uint64_t n;
+    const uint8_t *in;
+    const uint64_t *in_offsets;
+    uint8_t *out;
+    uint64_t out_capacity;
+    uint64_t *out_offsets;      // packed: produced by the scan; slotted: given
+    const uint64_t *out_caps;   // nullptr = packed
+    uint64_t *out_lens;         // never null inside the library (scratch when the caller passes NULL)
+    int32_t *status;            // optional
+    uint64_t *consumed;         // optional
+    uint32_t *overflow_pattern; // encode, optional
+    uint8_t *overflow_num_bits; // encode, optional
+    uint64_t *leftover_working_bits;  // decode, optional
+    uint8_t *leftover_num_bits;       // decode, optional
+};
+
+__device__ __forceinline__ uint32_t lane_id() {
+    return threadIdx.x & 31u;
+}
+
+__device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t *p) {
+    uint64_t v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void st_relaxed_u64(uint64_t *p, uint64_t v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Warp-inclusive scan of 32-bit values.
+__device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v) {
+    const uint32_t lane = lane_id();
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= (uint32_t)d) v += up;
+    }
+    return v;
+}
+
+__device__ __forceinline__ uint64_t warp_inclusive_scan64(uint64_t v) {
+    const uint32_t lane = lane_id();
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint64_t up = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= (uint32_t)d) v += up;
+    }
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Single-pass decoupled look-back (Merrill & Garland) over 64-bit sums.
+// One descriptor word per tile: [63:62] flag, [61:0] value.
+// ---------------------------------------------------------------------------------------------
+constexpr uint64_t kLbFlagShift = 62;
+constexpr uint64_t kLbValueMask = (1ull << 62) - 1;
+constexpr uint64_t kLbInvalid = 0;
+constexpr uint64_t kLbAggregate = 1;
+constexpr uint64_t kLbPrefix = 2;
+
+// Called by ONE FULL WARP of the tile's block. Publishes this tile's aggregate, walks back over
+// predecessors, publishes the inclusive prefix and returns the exclusive prefix to every lane.
+__device__ __forceinline__ uint64_t lookback_exclusive_prefix(uint64_t *tile_state, uint32_t tile, uint64_t aggregate) {
+    const uint32_t lane = lane_id();
+    if (tile == 0) {
+        if (lane == 0) st_relaxed_u64(&tile_state[0], (kLbPrefix << kLbFlagShift) | (aggregate & kLbValueMask));
+        return 0;
+    }
+    if (lane == 0) st_relaxed_u64(&tile_state[tile], (kLbAggregate << kLbFlagShift) | (aggregate & kLbValueMask));
+
+    uint64_t exclusive = 0;
+    int64_t look = (int64_t)tile - 1;  // highest predecessor of the current window
+    while (true) {
+        const int64_t idx = look - (int64_t)lane;
+        uint64_t word = (kLbPrefix << kLbFlagShift);  // lanes past tile 0 act as "prefix 0"
+        if (idx >= 0) {
+            do {
+                word = ld_relaxed_u64(&tile_state[idx]);
+            } while ((word >> kLbFlagShift) == kLbInvalid);
+        }
+        const uint32_t is_prefix = (word >> kLbFlagShift) == kLbPrefix;
+        const uint32_t prefix_mask = __ballot_sync(0xffffffffu, is_prefix);
+        // lanes at or below the first prefix lane contribute
+        const uint32_t first = prefix_mask ? (uint32_t)(__ffs(prefix_mask) - 1) : 32u;
+        uint64_t contrib = (lane <= first) ? (word & kLbValueMask) : 0;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
+        exclusive += contrib;
+        if (prefix_mask) break;
+        look -= 32;
+    }
+    if (lane == 0)
+        st_relaxed_u64(&tile_state[tile], (kLbPrefix << kLbFlagShift) | ((exclusive + aggregate) & kLbValueMask));
+    return exclusive;
+}
+
+}  // namespace hb

@@ -1,0 +1,502 @@
+// C-ABI of the batched Huffman codec (include/aws/compression/huffman_batch.h) and the host-side
+// orchestration around the CUDA kernels: context (device tables, stream, scratch), host<->device
+// staging for the host-pointer entry points, kernel selection and launch.
+//
+// No CPU fallback lives here: every failure to reach the device surfaces as
+// AWS_ERROR_COMPRESSION_DEVICE_FAILURE.
+#include <aws/compression/huffman_batch.h>
+
+#include "../host/huffman_lut.h"
+#include "device_common.cuh"
+#include "generic_kernels.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+namespace {
+
+using namespace hb;
+
+#define HB_CUDA_TRY(expr)                                                                                              \
+    do {                                                                                                               \
+        cudaError_t hb_err_ = (expr);                                                                                  \
+        if (hb_err_ != cudaSuccess) {                                                                                  \
+            hb_note_cuda_error(hb_err_, #expr, __LINE__);                                                              \
+            return aws_raise_error(AWS_ERROR_COMPRESSION_DEVICE_FAILURE);                                              \
+        }                                                                                                              \
+    } while (0)
+
+void hb_note_cuda_error(cudaError_t err, const char *what, int line) {
+    if (getenv("AWS_HUFFMAN_BATCH_DEBUG")) {
+        fprintf(stderr, "aws-c-compression(b200): %s failed at line %d: %s\n", what, line, cudaGetErrorString(err));
+    }
+    (void)cudaGetLastError(); /* clear the sticky-less error slot */
+}
+
+}  // namespace
+
+namespace hb_host {
+// Device buffer that only ever grows.
+struct GrowBuf {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+
+    cudaError_t reserve(size_t want) {
+        if (want <= bytes) return cudaSuccess;
+        size_t grown = std::max(want, bytes + bytes / 2);
+        grown = (grown + 255) & ~size_t(255);
+        void *fresh = nullptr;
+        cudaError_t err = cudaMalloc(&fresh, grown);
+        if (err != cudaSuccess) return err;
+        if (ptr) cudaFree(ptr);
+        ptr = fresh;
+        bytes = grown;
+        return cudaSuccess;
+    }
+    void release() {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        bytes = 0;
+    }
+    template <typename T>
+    T *as() const {
+        return static_cast<T *>(ptr);
+    }
+};
+}  // namespace hb_host
+using hb_host::GrowBuf;
+
+struct aws_huffman_batch_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    hb::DeviceTables tables{};
+    uint2 *d_enc = nullptr;
+    uint32_t *d_lut = nullptr;
+    uint32_t lut_smem_entries = 0;
+    uint64_t launches = 0;
+
+    // scratch for the device entry points
+    GrowBuf lens, tile_state;
+    // staging for the host entry points
+    GrowBuf s_in, s_in_off, s_out, s_out_off, s_caps, s_status, s_consumed, s_ovf_pattern, s_ovf_bits, s_left_bits,
+        s_left_num;
+};
+
+namespace {
+
+constexpr uint32_t kLutRootBits = 10;
+constexpr uint32_t kLutSubBits = 8;
+constexpr uint32_t kLutMaxSmemEntries = 8192;  // 32 KiB
+
+int check_batch(const aws_huffman_batch *b) {
+    if (!b) return aws_raise_error(AWS_ERROR_INVALID_ARGUMENT);
+    if (b->n == 0) return AWS_OP_SUCCESS;
+    if (!b->in_offsets || !b->out_offsets) return aws_raise_error(AWS_ERROR_INVALID_ARGUMENT);
+    return AWS_OP_SUCCESS;
+}
+
+hb::BatchView make_view(const aws_huffman_batch *b) {
+    hb::BatchView v{};
+    v.n = b->n;
+    v.in = b->in;
+    v.in_offsets = b->in_offsets;
+    v.out = b->out;
+    v.out_capacity = b->out_capacity;
+    v.out_offsets = b->out_offsets;
+    v.out_caps = b->out_caps;
+    v.out_lens = b->out_lens;
+    v.status = b->status;
+    v.consumed = b->consumed;
+    v.overflow_pattern = b->overflow_pattern;
+    v.overflow_num_bits = b->overflow_num_bits;
+    v.leftover_working_bits = b->leftover_working_bits;
+    v.leftover_num_bits = b->leftover_num_bits;
+    return v;
+}
+
+// lens -> offsets on the device
+int launch_scan(aws_huffman_batch_ctx *ctx, const uint64_t *lens, uint64_t *offsets, uint64_t n, cudaStream_t stream) {
+    const uint64_t tiles = std::max<uint64_t>(1, (n + kScanTile - 1) / kScanTile);
+    const size_t state_bytes = tiles * sizeof(uint64_t) + 256;
+    HB_CUDA_TRY(ctx->tile_state.reserve(state_bytes));
+    HB_CUDA_TRY(cudaMemsetAsync(ctx->tile_state.ptr, 0, state_bytes, stream));
+    uint64_t *state = ctx->tile_state.as<uint64_t>();
+    uint32_t *ticket = reinterpret_cast<uint32_t *>(state + tiles);
+    scan_lens_kernel<<<(unsigned)tiles, kScanThreads, 0, stream>>>(lens, offsets, n, state, ticket);
+    ++ctx->launches;
+    HB_CUDA_TRY(cudaGetLastError());
+    return AWS_OP_SUCCESS;
+}
+
+int encode_on_device(aws_huffman_batch_ctx *ctx, hb::BatchView v, cudaStream_t stream) {
+    if (v.n == 0) return AWS_OP_SUCCESS;
+    if (!v.out_lens) {
+        HB_CUDA_TRY(ctx->lens.reserve(v.n * sizeof(uint64_t)));
+        v.out_lens = ctx->lens.as<uint64_t>();
+    }
+    const unsigned blocks = (unsigned)((v.n + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    if (!v.out_caps) {
+        encode_items_warp_kernel<false><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(ctx->tables, v);
+        ++ctx->launches;
+        HB_CUDA_TRY(cudaGetLastError());
+        if (launch_scan(ctx, v.out_lens, v.out_offsets, v.n, stream)) return AWS_OP_ERR;
+    }
+    encode_items_warp_kernel<true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(ctx->tables, v);
+    ++ctx->launches;
+    HB_CUDA_TRY(cudaGetLastError());
+    return AWS_OP_SUCCESS;
+}
+
+int decode_on_device(aws_huffman_batch_ctx *ctx, hb::BatchView v, cudaStream_t stream) {
+    if (v.n == 0) return AWS_OP_SUCCESS;
+    if (!v.out_lens) {
+        HB_CUDA_TRY(ctx->lens.reserve(v.n * sizeof(uint64_t)));
+        v.out_lens = ctx->lens.as<uint64_t>();
+    }
+    const unsigned threads = 256;
+    const unsigned blocks = (unsigned)((v.n + threads - 1) / threads);
+    const size_t smem = ctx->lut_smem_entries * sizeof(uint32_t);
+    if (!v.out_caps) {
+        decode_items_thread_kernel<false><<<blocks, threads, smem, stream>>>(ctx->tables, v, ctx->lut_smem_entries);
+        ++ctx->launches;
+        HB_CUDA_TRY(cudaGetLastError());
+        if (launch_scan(ctx, v.out_lens, v.out_offsets, v.n, stream)) return AWS_OP_ERR;
+    }
+    decode_items_thread_kernel<true><<<blocks, threads, smem, stream>>>(ctx->tables, v, ctx->lut_smem_entries);
+    ++ctx->launches;
+    HB_CUDA_TRY(cudaGetLastError());
+    return AWS_OP_SUCCESS;
+}
+
+// Host-pointer entry point shared by encode and decode: stage in, run, stage out.
+int run_host_batch(aws_huffman_batch_ctx *ctx, const aws_huffman_batch *b, bool encode) {
+    if (!ctx) return aws_raise_error(AWS_ERROR_INVALID_ARGUMENT);
+    if (check_batch(b)) return AWS_OP_ERR;
+    const size_t n = b->n;
+    if (n == 0) {
+        if (!b->out_caps && b->out_offsets) b->out_offsets[0] = 0;
+        return AWS_OP_SUCCESS;
+    }
+    HB_CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const uint64_t total_in = b->in_offsets[n];
+    const bool slotted = b->out_caps != nullptr;
+    if ((total_in && !b->in) || (b->out_capacity && !b->out)) return aws_raise_error(AWS_ERROR_INVALID_ARGUMENT);
+
+    HB_CUDA_TRY(ctx->s_in.reserve(total_in + 16));
+    HB_CUDA_TRY(ctx->s_in_off.reserve((n + 1) * sizeof(uint64_t)));
+    HB_CUDA_TRY(ctx->s_out.reserve(b->out_capacity + 16));
+    HB_CUDA_TRY(ctx->s_out_off.reserve((n + 1) * sizeof(uint64_t)));
+    HB_CUDA_TRY(ctx->lens.reserve(n * sizeof(uint64_t)));
+    if (slotted) HB_CUDA_TRY(ctx->s_caps.reserve(n * sizeof(uint64_t)));
+    if (b->status) HB_CUDA_TRY(ctx->s_status.reserve(n * sizeof(int32_t)));
+    if (b->consumed) HB_CUDA_TRY(ctx->s_consumed.reserve(n * sizeof(uint64_t)));
+    if (encode && b->overflow_pattern) HB_CUDA_TRY(ctx->s_ovf_pattern.reserve(n * sizeof(uint32_t)));
+    if (encode && b->overflow_num_bits) HB_CUDA_TRY(ctx->s_ovf_bits.reserve(n));
+    if (!encode && b->leftover_working_bits) HB_CUDA_TRY(ctx->s_left_bits.reserve(n * sizeof(uint64_t)));
+    if (!encode && b->leftover_num_bits) HB_CUDA_TRY(ctx->s_left_num.reserve(n));
+
+    if (total_in) HB_CUDA_TRY(cudaMemcpyAsync(ctx->s_in.ptr, b->in, total_in, cudaMemcpyHostToDevice, st));
+    HB_CUDA_TRY(cudaMemcpyAsync(ctx->s_in_off.ptr, b->in_offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    if (slotted) {
+        HB_CUDA_TRY(cudaMemcpyAsync(ctx->s_out_off.ptr, b->out_offsets, n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        HB_CUDA_TRY(cudaMemcpyAsync(ctx->s_caps.ptr, b->out_caps, n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        // bytes the codec does not touch must come back unchanged
+        if (b->out_capacity)
+            HB_CUDA_TRY(cudaMemcpyAsync(ctx->s_out.ptr, b->out, b->out_capacity, cudaMemcpyHostToDevice, st));
+    }
+
+    hb::BatchView v{};
+    v.n = n;
+    v.in = ctx->s_in.as<uint8_t>();
+    v.in_offsets = ctx->s_in_off.as<uint64_t>();
+    v.out = ctx->s_out.as<uint8_t>();
+    v.out_capacity = b->out_capacity;
+    v.out_offsets = ctx->s_out_off.as<uint64_t>();
+    v.out_caps = slotted ? ctx->s_caps.as<uint64_t>() : nullptr;
+    v.out_lens = ctx->lens.as<uint64_t>();
+    v.status = b->status ? ctx->s_status.as<int32_t>() : nullptr;
+    v.consumed = b->consumed ? ctx->s_consumed.as<uint64_t>() : nullptr;
+    if (encode) {
+        v.overflow_pattern = b->overflow_pattern ? ctx->s_ovf_pattern.as<uint32_t>() : nullptr;
+        v.overflow_num_bits = b->overflow_num_bits ? ctx->s_ovf_bits.as<uint8_t>() : nullptr;
+    } else {
+        v.leftover_working_bits = b->leftover_working_bits ? ctx->s_left_bits.as<uint64_t>() : nullptr;
+        v.leftover_num_bits = b->leftover_num_bits ? ctx->s_left_num.as<uint8_t>() : nullptr;
+    }
+
+    if ((encode ? encode_on_device(ctx, v, st) : decode_on_device(ctx, v, st)) != AWS_OP_SUCCESS) return AWS_OP_ERR;
+
+    if (b->out_lens) HB_CUDA_TRY(cudaMemcpyAsync(b->out_lens, v.out_lens, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    if (b->status) HB_CUDA_TRY(cudaMemcpyAsync(b->status, v.status, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (b->consumed)
+        HB_CUDA_TRY(cudaMemcpyAsync(b->consumed, v.consumed, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    if (encode) {
+        if (b->overflow_pattern)
+            HB_CUDA_TRY(cudaMemcpyAsync(
+                b->overflow_pattern, v.overflow_pattern, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        if (b->overflow_num_bits)
+            HB_CUDA_TRY(cudaMemcpyAsync(b->overflow_num_bits, v.overflow_num_bits, n, cudaMemcpyDeviceToHost, st));
+    } else {
+        if (b->leftover_working_bits)
+            HB_CUDA_TRY(cudaMemcpyAsync(
+                b->leftover_working_bits, v.leftover_working_bits, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        if (b->leftover_num_bits)
+            HB_CUDA_TRY(cudaMemcpyAsync(b->leftover_num_bits, v.leftover_num_bits, n, cudaMemcpyDeviceToHost, st));
+    }
+
+    if (slotted) {
+        if (b->out_capacity)
+            HB_CUDA_TRY(cudaMemcpyAsync(b->out, v.out, b->out_capacity, cudaMemcpyDeviceToHost, st));
+        HB_CUDA_TRY(cudaStreamSynchronize(st));
+        return AWS_OP_SUCCESS;
+    }
+
+    HB_CUDA_TRY(
+        cudaMemcpyAsync(b->out_offsets, v.out_offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    HB_CUDA_TRY(cudaStreamSynchronize(st));
+    const uint64_t total_out = b->out_offsets[n];
+    if (total_out > b->out_capacity) return aws_raise_error(AWS_ERROR_SHORT_BUFFER);
+    if (total_out) {
+        HB_CUDA_TRY(cudaMemcpyAsync(b->out, v.out, total_out, cudaMemcpyDeviceToHost, st));
+        HB_CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    return AWS_OP_SUCCESS;
+}
+
+__global__ void encoded_length_kernel(hb::DeviceTables t, const uint8_t *in, const uint64_t *in_offsets, uint64_t n, uint64_t *lens) {
+    __shared__ uint32_t s_len[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_len[i] = t.enc[i].y;
+    __syncthreads();
+    const uint64_t item = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (item >= n) return;
+    const uint64_t a = in_offsets[item], e = in_offsets[item + 1];
+    uint64_t bits = 0;
+    for (uint64_t k = a + hb::lane_id(); k < e; k += 32) bits += s_len[in[k]];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) bits += __shfl_xor_sync(0xffffffffu, bits, d);
+    if (hb::lane_id() == 0) lens[item] = (bits + 7) >> 3;
+}
+
+}  // namespace
+
+extern "C" {
+
+int aws_huffman_batch_ctx_new(
+    struct aws_huffman_batch_ctx **out_ctx,
+    struct aws_huffman_symbol_coder *coder,
+    uint8_t eos_padding,
+    int device_id) {
+
+    if (!out_ctx || !coder || !coder->encode) return aws_raise_error(AWS_ERROR_INVALID_ARGUMENT);
+    *out_ctx = nullptr;
+
+    // Materialise the coder once over all 256 symbols (host callbacks never run again).
+    uint32_t patterns[256];
+    uint8_t num_bits[256];
+    uint2 enc[256];
+    for (int s = 0; s < 256; ++s) {
+        const struct aws_huffman_code c = coder->encode((uint8_t)s, coder->userdata);
+        if (c.num_bits > 32) return aws_raise_error(AWS_ERROR_COMPRESSION_INVALID_CODE_TABLE);
+        const uint32_t mask = c.num_bits >= 32 ? 0xffffffffu : ((1u << c.num_bits) - 1u);
+        patterns[s] = c.pattern & mask;
+        num_bits[s] = c.num_bits;
+        enc[s] = make_uint2(patterns[s], c.num_bits);
+    }
+    struct huffman_lut lut;
+    const int lut_rc = huffman_lut_build(&lut, patterns, num_bits, kLutRootBits, kLutSubBits);
+    if (lut_rc == HUFFMAN_LUT_ERR_OOM) return aws_raise_error(AWS_ERROR_OOM);
+    if (lut_rc != HUFFMAN_LUT_OK) return aws_raise_error(AWS_ERROR_COMPRESSION_INVALID_CODE_TABLE);
+
+    // Optional cross-check of the coder's own decode callback on every code (what the reference's
+    // huffman_symbol_decoder test does, tests/huffman_test.c:199-220).
+    if (coder->decode) {
+        for (int s = 0; s < 256; ++s) {
+            if (!num_bits[s]) continue;
+            uint8_t sym = 0;
+            const uint8_t used = coder->decode(patterns[s] << (32 - num_bits[s]), &sym, coder->userdata);
+            if (used != num_bits[s] || sym != s) {
+                huffman_lut_clean_up(&lut);
+                return aws_raise_error(AWS_ERROR_COMPRESSION_INVALID_CODE_TABLE);
+            }
+        }
+    }
+
+    aws_huffman_batch_ctx *ctx = new (std::nothrow) aws_huffman_batch_ctx();
+    if (!ctx) {
+        huffman_lut_clean_up(&lut);
+        return aws_raise_error(AWS_ERROR_OOM);
+    }
+    ctx->device = device_id;
+
+    auto fail = [&](cudaError_t err, const char *what, int line) {
+        hb_note_cuda_error(err, what, line);
+        huffman_lut_clean_up(&lut);
+        aws_huffman_batch_ctx_destroy(ctx);
+        return aws_raise_error(AWS_ERROR_COMPRESSION_DEVICE_FAILURE);
+    };
+#define HB_CTX_TRY(expr)                                                                                               \
+    do {                                                                                                               \
+        cudaError_t e_ = (expr);                                                                                       \
+        if (e_ != cudaSuccess) return fail(e_, #expr, __LINE__);                                                       \
+    } while (0)
+
+    int count = 0;
+    HB_CTX_TRY(cudaGetDeviceCount(&count));
+    if (device_id < 0 || device_id >= count) return fail(cudaErrorInvalidDevice, "device_id", __LINE__);
+    HB_CTX_TRY(cudaSetDevice(device_id));
+    HB_CTX_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    HB_CTX_TRY(cudaMalloc(&ctx->d_enc, sizeof(enc)));
+    HB_CTX_TRY(cudaMalloc(&ctx->d_lut, (size_t)lut.count * sizeof(uint32_t)));
+    HB_CTX_TRY(cudaMemcpy(ctx->d_enc, enc, sizeof(enc), cudaMemcpyHostToDevice));
+    HB_CTX_TRY(cudaMemcpy(ctx->d_lut, lut.entries, (size_t)lut.count * sizeof(uint32_t), cudaMemcpyHostToDevice));
+#undef HB_CTX_TRY
+
+    ctx->tables.enc = ctx->d_enc;
+    ctx->tables.lut = ctx->d_lut;
+    ctx->tables.lut_count = lut.count;
+    ctx->tables.lut_root_bits = lut.root_bits;
+    ctx->tables.min_len = lut.min_len;
+    ctx->tables.max_len = lut.max_len;
+    ctx->tables.has_unknown = lut.has_unknown_symbols;
+    ctx->tables.eos_padding = eos_padding;
+    ctx->lut_smem_entries = std::min<uint32_t>(lut.count, kLutMaxSmemEntries);
+    if (ctx->lut_smem_entries < (1u << lut.root_bits)) ctx->lut_smem_entries = 1u << lut.root_bits;
+    huffman_lut_clean_up(&lut);
+
+    *out_ctx = ctx;
+    return AWS_OP_SUCCESS;
+}
+
+void aws_huffman_batch_ctx_destroy(struct aws_huffman_batch_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamDestroy(ctx->stream);
+    }
+    if (ctx->d_enc) cudaFree(ctx->d_enc);
+    if (ctx->d_lut) cudaFree(ctx->d_lut);
+    GrowBuf *bufs[] = {&ctx->lens,     &ctx->tile_state, &ctx->s_in,       &ctx->s_in_off,      &ctx->s_out,
+                       &ctx->s_out_off, &ctx->s_caps,     &ctx->s_status,   &ctx->s_consumed,    &ctx->s_ovf_pattern,
+                       &ctx->s_ovf_bits, &ctx->s_left_bits, &ctx->s_left_num};
+    for (GrowBuf *g : bufs) g->release();
+    (void)cudaGetLastError();
+    delete ctx;
+}
+
+int aws_huffman_encode_batch(struct aws_huffman_batch_ctx *ctx, const struct aws_huffman_batch *batch) {
+    return run_host_batch(ctx, batch, true);
+}
+
+int aws_huffman_decode_batch(struct aws_huffman_batch_ctx *ctx, const struct aws_huffman_batch *batch) {
+    return run_host_batch(ctx, batch, false);
+}
+
+int aws_huffman_encode_batch_device(
+    struct aws_huffman_batch_ctx *ctx,
+    const struct aws_huffman_batch *batch,
+    void *cuda_stream) {
+    if (!ctx) return aws_raise_error(AWS_ERROR_INVALID_ARGUMENT);
+    if (check_batch(batch)) return AWS_OP_ERR;
+    HB_CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
+    return encode_on_device(ctx, make_view(batch), st);
+}
+
+int aws_huffman_decode_batch_device(
+    struct aws_huffman_batch_ctx *ctx,
+    const struct aws_huffman_batch *batch,
+    void *cuda_stream) {
+    if (!ctx) return aws_raise_error(AWS_ERROR_INVALID_ARGUMENT);
+    if (check_batch(batch)) return AWS_OP_ERR;
+    HB_CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
+    return decode_on_device(ctx, make_view(batch), st);
+}
+
+int aws_huffman_get_encoded_length_batch(
+    struct aws_huffman_batch_ctx *ctx,
+    const uint8_t *in,
+    const uint64_t *in_offsets,
+    size_t n,
+    uint64_t *lens) {
+    if (!ctx || (n && (!in_offsets || !lens))) return aws_raise_error(AWS_ERROR_INVALID_ARGUMENT);
+    if (n == 0) return AWS_OP_SUCCESS;
+    HB_CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const uint64_t total_in = in_offsets[n];
+    if (total_in && !in) return aws_raise_error(AWS_ERROR_INVALID_ARGUMENT);
+    HB_CUDA_TRY(ctx->s_in.reserve(total_in + 16));
+    HB_CUDA_TRY(ctx->s_in_off.reserve((n + 1) * sizeof(uint64_t)));
+    HB_CUDA_TRY(ctx->lens.reserve(n * sizeof(uint64_t)));
+    if (total_in) HB_CUDA_TRY(cudaMemcpyAsync(ctx->s_in.ptr, in, total_in, cudaMemcpyHostToDevice, st));
+    HB_CUDA_TRY(cudaMemcpyAsync(ctx->s_in_off.ptr, in_offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    const unsigned blocks = (unsigned)((n + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    encoded_length_kernel<<<blocks, kWarpsPerBlock * 32, 0, st>>>(
+        ctx->tables, ctx->s_in.as<uint8_t>(), ctx->s_in_off.as<uint64_t>(), n, ctx->lens.as<uint64_t>());
+    ++ctx->launches;
+    HB_CUDA_TRY(cudaGetLastError());
+    HB_CUDA_TRY(cudaMemcpyAsync(lens, ctx->lens.ptr, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    HB_CUDA_TRY(cudaStreamSynchronize(st));
+    return AWS_OP_SUCCESS;
+}
+
+int aws_huffman_batch_ctx_synchronize(struct aws_huffman_batch_ctx *ctx) {
+    if (!ctx) return aws_raise_error(AWS_ERROR_INVALID_ARGUMENT);
+    HB_CUDA_TRY(cudaSetDevice(ctx->device));
+    HB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return AWS_OP_SUCCESS;
+}
+
+void *aws_huffman_batch_ctx_stream(struct aws_huffman_batch_ctx *ctx) {
+    return ctx ? ctx->stream : nullptr;
+}
+
+int aws_huffman_batch_ctx_device(struct aws_huffman_batch_ctx *ctx) {
+    return ctx ? ctx->device : -1;
+}
+
+uint64_t aws_huffman_batch_ctx_launch_count(struct aws_huffman_batch_ctx *ctx) {
+    return ctx ? ctx->launches : 0;
+}
+
+int aws_huffman_batch_plan_shards(const uint64_t *in_offsets, size_t n, size_t num_shards, size_t *shard_begin) {
+    if (!shard_begin || num_shards == 0 || (n && !in_offsets)) return aws_raise_error(AWS_ERROR_INVALID_ARGUMENT);
+    const uint64_t base = n ? in_offsets[0] : 0;
+    const uint64_t total = n ? in_offsets[n] - base : 0;
+    shard_begin[0] = 0;
+    for (size_t s = 1; s < num_shards; ++s) {
+        // first item whose start offset reaches the s-th equal share of the bytes
+        const uint64_t target = base + (uint64_t)(((unsigned __int128)total * s) / num_shards);
+        const uint64_t *it = std::lower_bound(in_offsets, in_offsets + n, target);
+        size_t idx = (size_t)(it - in_offsets);
+        if (total == 0) idx = (size_t)(((unsigned __int128)n * s) / num_shards);  // all items empty: split by count
+        shard_begin[s] = std::max(idx, shard_begin[s - 1]);
+    }
+    shard_begin[num_shards] = n;
+    return AWS_OP_SUCCESS;
+}
+
+int aws_huffman_batch_concat_offsets(
+    const uint64_t *const *shard_offsets,
+    const size_t *shard_items,
+    size_t num_shards,
+    uint64_t *global_offsets) {
+    if (!global_offsets || (num_shards && (!shard_offsets || !shard_items)))
+        return aws_raise_error(AWS_ERROR_INVALID_ARGUMENT);
+    uint64_t base = 0;
+    size_t at = 0;
+    for (size_t s = 0; s < num_shards; ++s) {
+        const uint64_t *local = shard_offsets[s];
+        for (size_t i = 0; i < shard_items[s]; ++i) global_offsets[at++] = base + local[i];
+        if (shard_items[s]) base += local[shard_items[s]];
+    }
+    global_offsets[at] = base;
+    return AWS_OP_SUCCESS;
+}
+
+}  // extern "C"
