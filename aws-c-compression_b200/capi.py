@@ -29,6 +29,11 @@ ENCODE_FN = C.CFUNCTYPE(aws_huffman_code, C.c_uint8, C.c_void_p)
 DECODE_FN = C.CFUNCTYPE(C.c_uint8, C.c_uint32, C.POINTER(C.c_uint8), C.c_void_p)
 
 
+# ctypes cannot RETURN a struct from a Python callback. On x86-64 SysV an 8-byte integer-class struct
+# comes back in RAX, so a Python encode callback is declared as returning uint64 = pattern | bits << 32.
+ENCODE_FN_PY = C.CFUNCTYPE(C.c_uint64, C.c_uint8, C.c_void_p)
+
+
 class aws_huffman_symbol_coder(C.Structure):
     _fields_ = [("encode", ENCODE_FN), ("decode", DECODE_FN), ("userdata", C.c_void_p)]
 
@@ -68,6 +73,27 @@ class aws_huffman_batch(C.Structure):
         ("leftover_working_bits", C.c_void_p),
         ("leftover_num_bits", C.c_void_p),
     ]
+
+
+def python_coder(encode, decode=None):
+    """A symbol coder backed by Python callables (tests only).
+    encode(sym) -> (pattern, num_bits); decode(bits) -> (symbol, num_bits) or None."""
+    def enc_cb(sym, _):
+        pattern, nbits = encode(sym)
+        return (int(pattern) & 0xFFFFFFFF) | (int(nbits) << 32)
+
+    def dec_cb(bits, out_sym, _):
+        hit = decode(bits)
+        if not hit:
+            return 0
+        out_sym[0] = hit[0]
+        return hit[1]
+
+    enc_c = ENCODE_FN_PY(enc_cb)
+    dec_c = DECODE_FN(dec_cb) if decode else C.cast(None, DECODE_FN)
+    coder = aws_huffman_symbol_coder(C.cast(enc_c, ENCODE_FN), dec_c, None)
+    coder._keepalive = (enc_c, dec_c)
+    return coder
 
 
 assert C.sizeof(aws_huffman_code) == 8 and C.sizeof(aws_huffman_symbol_coder) == 24

@@ -52,3 +52,25 @@ def ref(pkg):
 def oracle_tables(oracle):
     import refcodec
     return {name: oracle.table(*refcodec.table_arrays(name)) for name in ("test", "hpack")}
+
+
+@pytest.fixture(scope="session")
+def ref_free_masked_coder(pkg, coders):
+    """A Python-callback coder (no reference needed): the test table with 8 symbols removed from
+    its ENCODE side. Returns (coder struct, patterns, num_bits)."""
+    import numpy as np
+    import refcodec
+    capi = pkg.capi
+    patterns, num_bits = refcodec.table_arrays("test")
+    num_bits = num_bits.copy()
+    num_bits[[0, 7, 65, 97, 101, 128, 200, 255]] = 0
+    inner = coders.coder("test").contents
+
+    def decode(bits):
+        import ctypes as C
+        tmp = C.c_uint8(0)
+        used = inner.decode(bits, C.byref(tmp), None)
+        return None if used == 0 or num_bits[tmp.value] == 0 else (tmp.value, used)
+
+    coder = capi.python_coder(lambda sym: (patterns[sym], num_bits[sym]), decode)
+    return coder, patterns, num_bits

@@ -1,0 +1,250 @@
+"""GPU parity: aws_huffman_encode_batch / aws_huffman_decode_batch (through the C ABI) against the
+oracle on the same seeded inputs, bit for bit — bytes, lengths, offsets, status, cursor positions and
+leftover encoder/decoder state — plus the committed outputs of the unmodified reference."""
+import numpy as np
+import pytest
+
+import refcodec
+from refcodec import OK, SHORT_BUFFER, UNKNOWN_SYMBOL
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def contexts(pkg, coders):
+    made = {}
+
+    def get(table, eos=0xFF):
+        key = (table, eos)
+        if key not in made:
+            made[key] = pkg.BatchContext(coders.coder(table), eos_padding=eos, device=0)
+        return made[key]
+
+    yield get
+    for ctx in made.values():
+        ctx.close()
+
+
+def assert_same(got, want, keys=None, total_key="out_offsets"):
+    for k in (keys or want.keys()):
+        if k == "out":
+            continue
+        assert np.array_equal(got[k], want[k]), "%s differs (first at %s)" % (
+            k, np.flatnonzero(np.asarray(got[k]) != np.asarray(want[k]))[:5])
+
+
+def assert_same_packed(got, want):
+    assert_same(got, want)
+    total = int(want["out_offsets"][-1])
+    assert np.array_equal(got["out"][:total], want["out"][:total]), "payload bytes differ"
+
+
+def assert_same_slotted(got, want, slots):
+    assert_same(got, want)
+    for i in np.random.default_rng(1).permutation(len(slots))[:4000]:
+        a, l = int(slots[i]), int(want["out_lens"][i])
+        assert np.array_equal(got["out"][a:a + l], want["out"][a:a + l]), "item %d bytes differ" % i
+
+
+def test_reference_golden_vectors_through_the_batch_api(contexts):
+    g = refcodec.golden("reference_vectors.json")
+    ctx = contexts("test")
+    ins = [bytes.fromhex(k["input_hex"]) for k in g["encode_kats"]] + [b"cdfh", b""]
+    want = [bytes.fromhex(k["encoded_hex"]) for k in g["encode_kats"]] + [bytes.fromhex("8218a3"), b""]
+    data = np.frombuffer(b"".join(ins), dtype=np.uint8)
+    offs = np.cumsum([0] + [len(x) for x in ins]).astype(np.uint64)
+    enc = ctx.encode(data, offs, 1024)
+    assert np.array_equal(enc["out_lens"], [len(w) for w in want])
+    assert bytes(enc["out"][:int(enc["out_offsets"][-1])]) == b"".join(want)
+    assert np.array_equal(ctx.encoded_lengths(data, offs), [len(w) for w in want])
+    dec = ctx.decode(enc["out"][:int(enc["out_offsets"][-1])], enc["out_offsets"], 1024)
+    assert np.array_equal(dec["out_offsets"], offs)
+    assert bytes(dec["out"][:len(data)]) == b"".join(ins)
+    assert (dec["status"] == OK).all() and (enc["status"] == OK).all()
+
+
+def test_rfc7541_vectors(contexts):
+    from test_oracle_pins import RFC7541_C
+    ctx = contexts("hpack")
+    data = np.frombuffer(b"".join(t for t, _ in RFC7541_C), dtype=np.uint8)
+    offs = np.cumsum([0] + [len(t) for t, _ in RFC7541_C]).astype(np.uint64)
+    enc = ctx.encode(data, offs, 4096)
+    assert bytes(enc["out"][:int(enc["out_offsets"][-1])]).hex() == "".join(h for _, h in RFC7541_C)
+
+
+@pytest.mark.parametrize("table_name", ["test", "hpack"])
+def test_committed_reference_outputs(contexts, pkg, table_name):
+    """Same fixture as the oracle pin test, now through the GPU: outputs of the unmodified reference."""
+    cases = refcodec.golden("differential_%s.json" % table_name)
+    plain = [c for c in cases["encode"] if not c["masked"]]
+    by_eos = {}
+    for c in plain:
+        by_eos.setdefault(c["eos"], []).append(c)
+    for eos, group in by_eos.items():
+        ctx = contexts(table_name, eos)
+        ins = [bytes.fromhex(c["in"]) for c in group]
+        data = np.frombuffer(b"".join(ins), dtype=np.uint8)
+        offs = np.cumsum([0] + [len(x) for x in ins]).astype(np.uint64)
+        caps = np.array([c["cap"] for c in group], dtype=np.uint64)
+        slots = np.zeros(len(group), dtype=np.uint64)
+        slots[1:] = np.cumsum(caps)[:-1]
+        r = ctx.encode(data, offs, int(caps.sum()) + 1, out_offsets=slots, out_caps=caps)
+        for i, c in enumerate(group):
+            a, l = int(slots[i]), int(r["out_lens"][i])
+            assert bytes(r["out"][a:a + l]).hex() == c["out"]
+            assert (int(r["status"][i]), int(r["consumed"][i]), int(r["overflow_pattern"][i]),
+                    int(r["overflow_num_bits"][i])) == (c["status"], c["consumed"], c["ovf_pattern"], c["ovf_bits"])
+    ctx = contexts(table_name)
+    group = cases["decode"]
+    ins = [bytes.fromhex(c["in"]) for c in group]
+    data = np.frombuffer(b"".join(ins), dtype=np.uint8)
+    offs = np.cumsum([0] + [len(x) for x in ins]).astype(np.uint64)
+    caps = np.array([c["cap"] for c in group], dtype=np.uint64)
+    slots = np.zeros(len(group), dtype=np.uint64)
+    slots[1:] = np.cumsum(caps)[:-1]
+    r = ctx.decode(data, offs, int(caps.sum()) + 1, out_offsets=slots, out_caps=caps)
+    for i, c in enumerate(group):
+        a, l = int(slots[i]), int(r["out_lens"][i])
+        assert bytes(r["out"][a:a + l]).hex() == c["out"]
+        assert (int(r["status"][i]), int(r["consumed"][i]), int(r["leftover_working_bits"][i]),
+                int(r["leftover_num_bits"][i])) == (c["status"], c["consumed"], c["left_bits"], c["left_num"])
+
+
+@pytest.mark.parametrize("table_name", ["test", "hpack"])
+@pytest.mark.parametrize("zipf", [True, False])
+def test_random_batches_match_oracle(contexts, oracle, oracle_tables, table_name, zipf):
+    rng = np.random.default_rng(0xB200 + zipf)
+    ctx, table = contexts(table_name), oracle_tables[table_name]
+    data, offs = refcodec.random_batch(rng, 20000, 0, 300, table_name, zipf=zipf)
+    n = len(offs) - 1
+    cap_total = 4 * len(data) + 16
+    want = oracle.encode_batch(table, 0xFF, data, offs, cap_total)
+    got = ctx.encode(data, offs, cap_total)
+    assert_same_packed(got, want)
+    assert np.array_equal(ctx.encoded_lengths(data, offs), want["out_lens"])
+
+    # slotted: capacities scattered around what each item needs
+    caps = np.maximum(0, want["out_lens"].astype(np.int64) + rng.integers(-8, 3, size=n)).astype(np.uint64)
+    slots = np.zeros(n, dtype=np.uint64)
+    slots[1:] = np.cumsum(caps)[:-1]
+    total = int(caps.sum()) + 1
+    sentinel = np.full(total, 0xA5, dtype=np.uint8)
+    want_s = oracle.encode_batch(table, 0xFF, data, offs, total, out_offsets=slots, out_caps=caps, out=sentinel.copy())
+    got_s = ctx.encode(data, offs, total, out_offsets=slots, out_caps=caps, out=sentinel.copy())
+    assert_same_slotted(got_s, want_s, slots)
+    assert np.array_equal(got_s["out"], want_s["out"]), "bytes outside the written prefixes must stay untouched"
+    assert (want_s["status"] == SHORT_BUFFER).any() and (want_s["status"] == OK).any()
+
+    # decode what was encoded (packed), then with limited capacities
+    stream = want["out"][:int(want["out_offsets"][-1])]
+    want_d = oracle.decode_batch(table, stream, want["out_offsets"], len(data) + 16)
+    got_d = ctx.decode(stream, want["out_offsets"], len(data) + 16)
+    assert_same_packed(got_d, want_d)
+    assert np.array_equal(got_d["out"][:len(data)], data)
+    caps = np.maximum(0, want_d["out_lens"].astype(np.int64) + rng.integers(-6, 2, size=n)).astype(np.uint64)
+    slots = np.zeros(n, dtype=np.uint64)
+    slots[1:] = np.cumsum(caps)[:-1]
+    total = int(caps.sum()) + 1
+    want_ds = oracle.decode_batch(table, stream, want["out_offsets"], total, out_offsets=slots, out_caps=caps)
+    got_ds = ctx.decode(stream, want["out_offsets"], total, out_offsets=slots, out_caps=caps)
+    assert_same_slotted(got_ds, want_ds, slots)
+
+
+@pytest.mark.parametrize("table_name", ["test", "hpack"])
+def test_decode_of_arbitrary_bytes_matches_oracle(contexts, oracle, oracle_tables, table_name):
+    """The reference's decode fuzzer (tests/fuzz/decode.c) as a differential test."""
+    rng = np.random.default_rng(0xF022)
+    ctx, table = contexts(table_name), oracle_tables[table_name]
+    lens = rng.integers(0, 120, size=20000)
+    offs = np.zeros(len(lens) + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum(lens)
+    payload = rng.integers(0, 256, size=int(offs[-1]), dtype=np.uint8)
+    payload[rng.random(len(payload)) < 0.3] = 0xFF  # long runs of ones reach the deep / invalid codes
+    cap = 2 * len(payload) + 16
+    want = oracle.decode_batch(table, payload, offs, cap)
+    got = ctx.decode(payload, offs, cap)
+    assert_same_packed(got, want)
+    assert (want["status"] == UNKNOWN_SYMBOL).any() and (want["status"] == OK).any()
+
+
+def test_unknown_symbols_on_encode(pkg, oracle, ref_free_masked_coder):
+    """A coder whose ENCODE table has holes: UNKNOWN_SYMBOL, truncated lengths, cursor past the symbol."""
+    coder, patterns, num_bits = ref_free_masked_coder
+    ctx = pkg.BatchContext(coder, device=0)
+    table = oracle.table(patterns, num_bits)
+    rng = np.random.default_rng(5)
+    data, offs = refcodec.random_batch(rng, 8000, 0, 120, "test", zipf=False)
+    cap_total = 4 * len(data) + 16
+    want = oracle.encode_batch(table, 0x3C, data, offs, cap_total)
+    ctx2 = pkg.BatchContext(coder, eos_padding=0x3C, device=0)
+    got = ctx2.encode(data, offs, cap_total)
+    assert_same_packed(got, want)
+    assert (want["status"] == UNKNOWN_SYMBOL).sum() > 100
+    n = len(offs) - 1
+    caps = np.maximum(0, want["out_lens"].astype(np.int64) + rng.integers(-4, 3, size=n)).astype(np.uint64)
+    slots = np.zeros(n, dtype=np.uint64)
+    slots[1:] = np.cumsum(caps)[:-1]
+    total = int(caps.sum()) + 1
+    want_s = oracle.encode_batch(table, 0x3C, data, offs, total, out_offsets=slots, out_caps=caps)
+    got_s = ctx2.encode(data, offs, total, out_offsets=slots, out_caps=caps)
+    assert_same_slotted(got_s, want_s, slots)
+    ctx.close()
+    ctx2.close()
+
+
+def test_full_range_code_lengths(pkg, oracle):
+    """Codes of 1, 31 and 32 bits (reference MAX_PATTERN_BITS, huffman.c:10)."""
+    import ctypes as C
+    capi = pkg.capi
+    patterns = np.zeros(256, dtype=np.uint32)
+    num_bits = np.zeros(256, dtype=np.uint8)
+    # 0 -> '0' (1 bit); 1 -> '10'; 2 -> 110 + 28 zeros (31 bits); 3 -> 111 + 29 zeros (32); 4 -> 111 + 28 zeros + 1 (32)
+    patterns[0], num_bits[0] = 0b0, 1
+    patterns[1], num_bits[1] = 0b10, 2
+    patterns[2], num_bits[2] = 0b110 << 28, 31
+    patterns[3], num_bits[3] = 0b111 << 29, 32
+    patterns[4], num_bits[4] = (0b111 << 29) | 1, 32
+    table = oracle.table(patterns, num_bits)
+
+    coder = capi.python_coder(lambda sym: (patterns[sym], num_bits[sym]))
+    ctx = pkg.BatchContext(coder, eos_padding=0xFF, device=0)
+    rng = np.random.default_rng(11)
+    lens = rng.integers(0, 200, size=3000)
+    offs = np.zeros(len(lens) + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum(lens)
+    data = rng.integers(0, 5, size=int(offs[-1])).astype(np.uint8)
+    cap_total = 4 * len(data) + 16
+    want = oracle.encode_batch(table, 0xFF, data, offs, cap_total)
+    got = ctx.encode(data, offs, cap_total)
+    assert_same_packed(got, want)
+    stream = want["out"][:int(want["out_offsets"][-1])]
+    want_d = oracle.decode_batch(table, stream, want["out_offsets"], 8 * len(stream) + 16)
+    got_d = ctx.decode(stream, want["out_offsets"], 8 * len(stream) + 16)
+    assert_same_packed(got_d, want_d)
+    n = len(lens)
+    caps = np.maximum(0, want["out_lens"].astype(np.int64) + rng.integers(-9, 2, size=n)).astype(np.uint64)
+    slots = np.zeros(n, dtype=np.uint64)
+    slots[1:] = np.cumsum(caps)[:-1]
+    total = int(caps.sum()) + 1
+    assert_same_slotted(ctx.encode(data, offs, total, out_offsets=slots, out_caps=caps),
+                        oracle.encode_batch(table, 0xFF, data, offs, total, out_offsets=slots, out_caps=caps), slots)
+    ctx.close()
+
+
+def test_packed_output_too_small_is_a_call_level_short_buffer(contexts, pkg):
+    ctx = contexts("hpack")
+    data = np.frombuffer(b"www.example.com" * 10, dtype=np.uint8)
+    offs = np.arange(0, 151, 15, dtype=np.uint64)
+    with pytest.raises(pkg.CodecError) as err:
+        ctx.encode(data, offs, out_capacity=20)
+    assert err.value.code == pkg.AWS_ERROR_SHORT_BUFFER
+
+
+def test_empty_batches_and_empty_items(contexts):
+    ctx = contexts("hpack")
+    r = ctx.encode(np.zeros(0, dtype=np.uint8), np.zeros(1, dtype=np.uint64), 16)
+    assert int(r["out_offsets"][0]) == 0
+    r = ctx.encode(np.zeros(0, dtype=np.uint8), np.zeros(6, dtype=np.uint64), 16)
+    assert not r["out_lens"].any() and not r["status"].any() and not r["out_offsets"].any()
+    r = ctx.decode(np.zeros(0, dtype=np.uint8), np.zeros(6, dtype=np.uint64), 16)
+    assert not r["out_lens"].any() and not r["status"].any()
