@@ -61,6 +61,7 @@ class aws_huffman_batch(C.Structure):
         ("n", C.c_size_t),
         ("in_", C.c_void_p),
         ("in_offsets", C.c_void_p),
+        ("in_size", C.c_uint64),
         ("out", C.c_void_p),
         ("out_capacity", C.c_uint64),
         ("out_offsets", C.c_void_p),
@@ -300,9 +301,10 @@ class BatchContext:
         if self.library.lib.aws_huffman_batch_ctx_synchronize(self.handle) != 0:
             raise CodecError(self.library.last_error(), "aws_huffman_batch_ctx_synchronize")
 
-    def _call(self, fn_name, n, arrays, out_capacity, stream=None):
+    def _call(self, fn_name, n, arrays, out_capacity, stream=None, in_size=0):
         b = aws_huffman_batch()
         b.n = n
+        b.in_size = in_size
         b.out_capacity = out_capacity
         for key, value in arrays.items():
             setattr(b, key, _ptr(value))
@@ -357,8 +359,10 @@ class BatchContext:
         return lens
 
     # ---- device-buffer entry points (torch CUDA tensors; enqueued on `stream`) ----
-    def encode_device(self, n, arrays, out_capacity, stream=None):
-        self._call("aws_huffman_encode_batch_device", n, arrays, int(out_capacity), stream=stream or 0)
+    def encode_device(self, n, arrays, in_size, out_capacity, stream=None):
+        self._call("aws_huffman_encode_batch_device", n, arrays, int(out_capacity), stream=stream or 0,
+                   in_size=int(in_size))
 
-    def decode_device(self, n, arrays, out_capacity, stream=None):
-        self._call("aws_huffman_decode_batch_device", n, arrays, int(out_capacity), stream=stream or 0)
+    def decode_device(self, n, arrays, in_size, out_capacity, stream=None):
+        self._call("aws_huffman_decode_batch_device", n, arrays, int(out_capacity), stream=stream or 0,
+                   in_size=int(in_size))

@@ -1,0 +1,394 @@
+// Tiled, symbol-parallel Huffman encode for the packed layout (BASELINE configs 2, 3, 5).
+//
+// The whole batch is treated as ONE run of input bytes cut into fixed tiles of kEncTile symbols; a
+// block owns a tile regardless of where item boundaries fall, so loads are 128-bit and coalesced
+// and every lane has work. Per tile:
+//
+//   A. each thread loads 16 symbols (one uint4), looks the code lengths up in shared memory and
+//      reduces them to a "segment function"  p -> p + head            (no item starts in its range)
+//                                            p -> ceil8(p + head) + tail   (items start in its range;
+//      an item start byte-aligns the output because the previous item is padded, huffman.c:178-184)
+//   B. warp-shuffle scan + block scan of those functions; one warp runs a single-pass decoupled
+//      look-back over tile descriptors to get the absolute output bit position G of the tile
+//   C. each thread re-reads its codes and packs them MSB-first into a shared-memory staging buffer
+//      at its exact bit position with a 64-bit funnel accumulator; words shared with a neighbour are
+//      merged with shared-memory atomicOr, interior words are plain stores
+//   D. the staged bytes this tile owns (those whose first bit lies in the tile) are copied to global
+//      memory with 128-bit stores. The bits that complete the tile's last byte belong to the next
+//      tile's first symbols (or to the EOS padding); one thread recomputes them from the input, so
+//      tiles never write the same byte and no global atomics or pre-zeroed output are needed.
+//
+// Only used when every symbol has a code (no UNKNOWN_SYMBOL possible); otherwise the generic kernel
+// runs. Results are bit-identical to the generic kernel and therefore to the reference.
+#pragma once
+
+#include "device_common.cuh"
+
+namespace hb {
+
+constexpr int kEncThreads = 256;
+constexpr int kEncSymsPerThread = 16;
+constexpr int kEncTile = kEncThreads * kEncSymsPerThread;  // 4096 input bytes
+constexpr int kEncStageBytes = kEncTile * 4 + 64;          // worst case 32 bits/symbol (+ alignment slack)
+
+// p -> hb ? ceil8(p + head) + tail : p + head
+struct Seg {
+    uint32_t head, tail, hb;
+};
+struct Seg64 {
+    uint64_t head, tail;
+    uint32_t hb;
+};
+
+__device__ __forceinline__ Seg seg_combine(const Seg &l, const Seg &r) {  // l first, then r
+    const uint32_t x = l.tail + r.head;
+    const uint32_t xr = r.hb ? ((x + 7u) & ~7u) : x;
+    Seg o;
+    o.head = l.hb ? l.head : l.head + r.head;
+    o.tail = l.hb ? xr + r.tail : r.tail;
+    o.hb = l.hb | r.hb;
+    return o;
+}
+__device__ __forceinline__ Seg64 seg_combine64(const Seg64 &l, const Seg64 &r) {
+    const uint64_t x = l.tail + r.head;
+    const uint64_t xr = r.hb ? ((x + 7ull) & ~7ull) : x;
+    Seg64 o;
+    o.head = l.hb ? l.head : l.head + r.head;
+    o.tail = l.hb ? xr + r.tail : r.tail;
+    o.hb = l.hb | r.hb;
+    return o;
+}
+__device__ __forceinline__ uint64_t seg_apply(const Seg &f, uint64_t p) {
+    return f.hb ? ((p + f.head + 7ull) & ~7ull) + f.tail : p + f.head;
+}
+__device__ __forceinline__ uint64_t seg_apply64(const Seg64 &f, uint64_t p) {
+    return f.hb ? ((p + f.head + 7ull) & ~7ull) + f.tail : p + f.head;
+}
+__device__ __forceinline__ Seg seg_shfl_up(const Seg &v, int d) {
+    Seg o;
+    o.head = __shfl_up_sync(0xffffffffu, v.head, d);
+    o.tail = __shfl_up_sync(0xffffffffu, v.tail, d);
+    o.hb = __shfl_up_sync(0xffffffffu, v.hb, d);
+    return o;
+}
+
+// Tile descriptor word: [63:62] status. Aggregate: [61] hb, [60:31] head, [30:0] tail (a tile's own
+// function). Prefix: [61:0] absolute output bit position at the END of the tile.
+__device__ __forceinline__ uint64_t seg_pack_aggregate(const Seg &f) {
+    return (kLbAggregate << kLbFlagShift) | ((uint64_t)f.hb << 61) | ((uint64_t)f.head << 31) | (uint64_t)f.tail;
+}
+
+// One full warp. Publishes the tile's function, resolves the absolute start position G of the tile by
+// walking back to the nearest tile whose end position is known, publishes this tile's end position.
+__device__ __forceinline__ uint64_t seg_lookback(uint64_t *tile_state, uint32_t tile, const Seg &agg) {
+    const uint32_t lane = lane_id();
+    uint64_t G = 0;
+    if (tile != 0) {
+        if (lane == 0) st_relaxed_u64(&tile_state[tile], seg_pack_aggregate(agg));
+        Seg64 acc = {0, 0, 0};  // function of tiles (look+1 .. tile-1), identity so far
+        int64_t look = (int64_t)tile - 1;
+        while (true) {
+            const int64_t idx = look - (int64_t)lane;
+            uint64_t word = kLbPrefix << kLbFlagShift;  // "tile -1" ends at bit 0
+            if (idx >= 0) {
+                do {
+                    word = ld_relaxed_u64(&tile_state[idx]);
+                } while ((word >> kLbFlagShift) == kLbInvalid);
+            }
+            const bool is_prefix = (word >> kLbFlagShift) == kLbPrefix;
+            const uint32_t pmask = __ballot_sync(0xffffffffu, is_prefix);
+            const uint32_t first = pmask ? (uint32_t)(__ffs(pmask) - 1) : 32u;
+            Seg64 f = {0, 0, 0};
+            if (lane < first) {
+                f.hb = (uint32_t)(word >> 61) & 1u;
+                f.head = (word >> 31) & 0x3FFFFFFFull;
+                f.tail = word & 0x7FFFFFFFull;
+            }
+            // ordered reduction: higher lanes hold EARLIER tiles
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                Seg64 o;
+                o.head = __shfl_down_sync(0xffffffffu, f.head, d);
+                o.tail = __shfl_down_sync(0xffffffffu, f.tail, d);
+                o.hb = __shfl_down_sync(0xffffffffu, f.hb, d);
+                if (lane + d < 32) f = seg_combine64(o, f);
+            }
+            Seg64 window;
+            window.head = __shfl_sync(0xffffffffu, f.head, 0);
+            window.tail = __shfl_sync(0xffffffffu, f.tail, 0);
+            window.hb = __shfl_sync(0xffffffffu, f.hb, 0);
+            acc = seg_combine64(window, acc);
+            if (pmask) {
+                const uint64_t end_of_known = __shfl_sync(0xffffffffu, word & kLbValueMask, first);
+                G = seg_apply64(acc, end_of_known);
+                break;
+            }
+            look -= 32;
+        }
+    }
+    if (lane == 0) st_relaxed_u64(&tile_state[tile], (kLbPrefix << kLbFlagShift) | (seg_apply(agg, G) & kLbValueMask));
+    return G;
+}
+
+// tile_first[j] = first item whose start offset is >= min(j * kEncTile, total_in), for j in [0, num_tiles]
+// (so tile_first[num_tiles] is the first trailing empty item, or n)
+__global__ void tile_index_kernel(
+    const uint64_t *in_offsets, uint64_t n, uint64_t total_in, uint64_t num_tiles, uint32_t *tile_first) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j > num_tiles) return;
+    const uint64_t target = min(j * (uint64_t)kEncTile, total_in);
+    uint64_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (in_offsets[mid] < target) lo = mid + 1; else hi = mid;
+    }
+    tile_first[j] = (uint32_t)lo;
+}
+
+struct EncTiledArgs {
+    const uint8_t *in;
+    const uint64_t *in_offsets;
+    uint64_t n;
+    uint64_t total_in;
+    uint8_t *out;
+    uint64_t out_capacity;
+    uint64_t *out_offsets;
+    const uint32_t *tile_first;  // kSeg only
+    uint64_t *tile_state;
+    uint32_t *ticket;
+    uint32_t num_tiles;
+    uint32_t eos_padding;
+};
+
+template <bool kSeg>
+__global__ void __launch_bounds__(kEncThreads) encode_tiled_kernel(const uint2 *__restrict__ enc_table, EncTiledArgs a) {
+    __shared__ uint2 s_tab[256];
+    __shared__ uint32_t s_mask[kEncTile / 32];
+    __shared__ uint32_t s_first_item[kEncThreads];
+    __shared__ Seg s_warp[kEncThreads / 32];
+    __shared__ uint32_t s_tile;
+    __shared__ uint64_t s_G, s_Gend;
+    __shared__ __align__(16) uint32_t s_stage[kEncStageBytes / 4];
+
+    const uint32_t tid = threadIdx.x;
+    const uint32_t lane = tid & 31, warp = tid >> 5;
+
+    if (tid == 0) s_tile = atomicAdd(a.ticket, 1u);
+    s_tab[tid] = enc_table[tid];
+    if (kSeg) {
+        if (tid < kEncTile / 32) s_mask[tid] = 0;
+        s_first_item[tid] = 0xffffffffu;
+    }
+    {
+        uint4 *z = reinterpret_cast<uint4 *>(s_stage);
+        for (uint32_t i = tid; i < kEncStageBytes / 16; i += kEncThreads) z[i] = make_uint4(0, 0, 0, 0);
+    }
+    __syncthreads();
+
+    const uint32_t tile = s_tile;
+    const uint64_t t0 = (uint64_t)tile * kEncTile;
+    const uint64_t t1 = min(t0 + (uint64_t)kEncTile, a.total_in);
+    const uint64_t p0 = t0 + (uint64_t)tid * kEncSymsPerThread;
+    const uint32_t nsym = p0 >= t1 ? 0u : (uint32_t)min((uint64_t)kEncSymsPerThread, t1 - p0);
+
+    // ---- load 16 symbols -------------------------------------------------------------------------
+    uint32_t w[4] = {0, 0, 0, 0};
+    if (nsym == kEncSymsPerThread && ((reinterpret_cast<uintptr_t>(a.in) & 15) == 0)) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(a.in + p0);
+        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < kEncSymsPerThread; ++k)
+            if ((uint32_t)k < nsym) w[k >> 2] |= (uint32_t)a.in[p0 + k] << (8 * (k & 3));
+    }
+
+    // ---- item starts inside the tile ------------------------------------------------------------------
+    uint32_t first_in_tile = 0, end_in_tile = 0;
+    if (kSeg) {
+        first_in_tile = a.tile_first[tile];
+        end_in_tile = a.tile_first[tile + 1];
+        for (uint32_t i = first_in_tile + tid; i < end_in_tile; i += kEncThreads) {
+            const uint32_t p = (uint32_t)(a.in_offsets[i] - t0);
+            atomicOr(&s_mask[p >> 5], 1u << (p & 31));
+            atomicMin(&s_first_item[p >> 4], i);
+        }
+        __syncthreads();
+    }
+    const uint32_t m = kSeg ? ((s_mask[tid >> 1] >> ((tid & 1) * 16)) & 0xffffu) : 0u;
+
+    // ---- A: the thread's segment function -------------------------------------------------------------
+    Seg mine = {0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < kEncSymsPerThread; ++k) {
+        const uint32_t sym = (w[k >> 2] >> (8 * (k & 3))) & 0xffu;
+        const uint32_t len = (uint32_t)k < nsym ? s_tab[sym].y : 0u;
+        if (kSeg) {
+            if ((m >> k) & 1u) {
+                if (mine.hb) mine.tail = (mine.tail + 7u) & ~7u;
+                mine.hb = 1;
+            }
+            if (mine.hb) mine.tail += len; else mine.head += len;
+        } else {
+            mine.head += len;
+        }
+    }
+
+    // ---- B: block scan of functions + look-back -----------------------------------------------------
+    Seg incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const Seg up = seg_shfl_up(incl, d);
+        if (lane >= (uint32_t)d) incl = seg_combine(up, incl);
+    }
+    Seg excl = seg_shfl_up(incl, 1);
+    if (lane == 0) excl = Seg{0, 0, 0};
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        Seg wv = lane < kEncThreads / 32 ? s_warp[lane] : Seg{0, 0, 0};
+        Seg wi = wv;
+#pragma unroll
+        for (int d = 1; d < kEncThreads / 32; d <<= 1) {
+            const Seg up = seg_shfl_up(wi, d);
+            if (lane >= (uint32_t)d) wi = seg_combine(up, wi);
+        }
+        Seg we = seg_shfl_up(wi, 1);
+        if (lane == 0) we = Seg{0, 0, 0};
+        Seg total;
+        total.head = __shfl_sync(0xffffffffu, wi.head, kEncThreads / 32 - 1);
+        total.tail = __shfl_sync(0xffffffffu, wi.tail, kEncThreads / 32 - 1);
+        total.hb = __shfl_sync(0xffffffffu, wi.hb, kEncThreads / 32 - 1);
+        if (lane < kEncThreads / 32) s_warp[lane] = we;  // exclusive per-warp functions
+        const uint64_t G = seg_lookback(a.tile_state, tile, total);
+        if (lane == 0) {
+            s_G = G;
+            s_Gend = seg_apply(total, G);
+        }
+    }
+    __syncthreads();
+
+    const uint64_t G = s_G, Gend = s_Gend;
+    const uint64_t P = seg_apply(excl, seg_apply(s_warp[warp], G));  // absolute bit position of my first code
+
+    // Staging origin: stage byte 0 <-> global address (out + G/8) rounded down to 16 bytes.
+    const uint64_t g_byte0 = G >> 3;
+    const uint32_t misalign = (uint32_t)((reinterpret_cast<uintptr_t>(a.out) + g_byte0) & 15);
+    const int64_t origin_byte = (int64_t)g_byte0 - (int64_t)misalign;  // absolute output byte of stage byte 0
+
+    // ---- C: pack my codes into the stage --------------------------------------------------------------
+    {
+        const uint32_t q = (uint32_t)((int64_t)P - origin_byte * 8);  // stage bit index of my first bit
+        uint32_t widx = q >> 5;
+        uint32_t nb = q & 31;          // bits in acc, counting the phantom bits of the shared first word
+        uint64_t acc = 0;
+        bool shared_word = nb != 0;    // my first word also holds a neighbour's bits
+        uint32_t cur_item = kSeg ? s_first_item[tid] : 0u;
+
+        auto append = [&](uint32_t code, uint32_t len) {
+            acc = (acc << len) | code;
+            nb += len;
+            if (nb >= 32) {
+                nb -= 32;
+                const uint32_t word = __byte_perm((uint32_t)(acc >> nb), 0, 0x0123);  // stream order in memory
+                if (shared_word) {
+                    atomicOr(&s_stage[widx], word);
+                    shared_word = false;
+                } else {
+                    s_stage[widx] = word;
+                }
+                ++widx;
+            }
+        };
+
+#pragma unroll
+        for (int k = 0; k < kEncSymsPerThread; ++k) {
+            if ((uint32_t)k < nsym) {
+                if (kSeg && ((m >> k) & 1u)) {
+                    // an item starts here: pad the previous one to a byte boundary, then record where
+                    // this item (and any empty items sharing its start) begins in the output
+                    const uint32_t pad = (8u - (nb & 7u)) & 7u;
+                    if (pad) append(a.eos_padding & ((1u << pad) - 1u), pad);
+                    const uint64_t ob = (uint64_t)(origin_byte + (int64_t)(((uint64_t)widx * 32 + nb) >> 3));
+                    const uint64_t here = p0 + k;
+                    do {
+                        a.out_offsets[cur_item] = ob;
+                        ++cur_item;
+                    } while (cur_item < a.n && a.in_offsets[cur_item] == here);
+                }
+                const uint32_t sym = (w[k >> 2] >> (8 * (k & 3))) & 0xffu;
+                const uint2 e = s_tab[sym];
+                append(e.x, e.y);
+            }
+        }
+        if (nb) atomicOr(&s_stage[widx], __byte_perm((uint32_t)(acc << (32 - nb)), 0, 0x0123));
+    }
+
+    // ---- the bits that complete this tile's last byte ------------------------------------------------
+    const bool last_tile = tile + 1 == a.num_tiles;
+    if (tid == 0) {
+        const uint32_t need = (8u - (uint32_t)(Gend & 7u)) & 7u;
+        if (need) {
+            uint64_t stop = a.total_in;  // where the open item ends
+            if (kSeg && end_in_tile < a.n) stop = a.in_offsets[end_in_tile];
+            uint32_t bits = 0, have = 0;
+            for (uint64_t p = t1; have < need && p < stop; ++p) {
+                const uint2 e = s_tab[a.in[p]];
+                const uint32_t take = min(e.y, need - have);
+                bits = (bits << take) | (e.x >> (e.y - take));
+                have += take;
+            }
+            if (have < need) {
+                const uint32_t rem = need - have;
+                bits = (bits << rem) | (a.eos_padding & ((1u << rem) - 1u));
+            }
+            const uint32_t sbyte = (uint32_t)((int64_t)(Gend >> 3) - origin_byte);
+            atomicOr(&s_stage[sbyte >> 2], bits << (8 * (sbyte & 3)));
+        }
+        if (!kSeg && tile == 0) a.out_offsets[0] = 0;
+        if (last_tile) {
+            const uint64_t total_out = (Gend + 7) >> 3;
+            a.out_offsets[a.n] = total_out;
+            if (kSeg) {
+                // trailing empty items start at total_in
+                for (uint64_t i = end_in_tile; i < a.n; ++i) a.out_offsets[i] = total_out;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- D: copy the bytes this tile owns ------------------------------------------------------------------
+    {
+        const uint64_t own_lo = (G + 7) >> 3, own_hi = min((Gend + 7) >> 3, a.out_capacity);
+        if (own_hi > own_lo) {
+            const uint32_t s_lo = (uint32_t)((int64_t)own_lo - origin_byte);
+            const uint32_t s_hi = (uint32_t)((int64_t)own_hi - origin_byte);
+            uint8_t *gbase = a.out + origin_byte;  // 16-byte aligned address of stage byte 0
+            const uint8_t *sb = reinterpret_cast<const uint8_t *>(s_stage);
+            const uint32_t v_lo = (s_lo + 15) & ~15u, v_hi = s_hi & ~15u;
+            if (v_lo < v_hi) {
+                for (uint32_t i = s_lo + tid; i < v_lo; i += kEncThreads) gbase[i] = sb[i];
+                const uint4 *s4 = reinterpret_cast<const uint4 *>(s_stage);
+                uint4 *g4 = reinterpret_cast<uint4 *>(gbase);
+                for (uint32_t i = (v_lo >> 4) + tid; i < (v_hi >> 4); i += kEncThreads) g4[i] = s4[i];
+                for (uint32_t i = v_hi + tid; i < s_hi; i += kEncThreads) gbase[i] = sb[i];
+            } else {
+                for (uint32_t i = s_lo + tid; i < s_hi; i += kEncThreads) gbase[i] = sb[i];
+            }
+        }
+    }
+}
+
+// Optional per-item arrays in the packed layout when no symbol can be unknown: every item succeeds.
+__global__ void fill_packed_meta_kernel(
+    uint64_t n, const uint64_t *in_offsets, const uint64_t *out_offsets, uint64_t *out_lens, int32_t *status,
+    uint64_t *consumed, uint32_t *overflow_pattern, uint8_t *overflow_num_bits) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (out_lens) out_lens[i] = out_offsets[i + 1] - out_offsets[i];
+    if (status) status[i] = kStatusOk;
+    if (consumed) consumed[i] = in_offsets[i + 1] - in_offsets[i];
+    if (overflow_pattern) overflow_pattern[i] = 0;
+    if (overflow_num_bits) overflow_num_bits[i] = 0;
+}
+
+}  // namespace hb

@@ -9,6 +9,7 @@
 #include "../host/huffman_lut.h"
 #include "device_common.cuh"
 #include "generic_kernels.cuh"
+#include "encode_tiled.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -79,7 +80,7 @@ struct aws_huffman_batch_ctx {
     uint64_t launches = 0;
 
     // scratch for the device entry points
-    GrowBuf lens, tile_state;
+    GrowBuf lens, tile_state, tile_first;
     // staging for the host entry points
     GrowBuf s_in, s_in_off, s_out, s_out_off, s_caps, s_status, s_consumed, s_ovf_pattern, s_ovf_bits, s_left_bits,
         s_left_num;
@@ -131,8 +132,54 @@ int launch_scan(aws_huffman_batch_ctx *ctx, const uint64_t *lens, uint64_t *offs
     return AWS_OP_SUCCESS;
 }
 
-int encode_on_device(aws_huffman_batch_ctx *ctx, hb::BatchView v, cudaStream_t stream) {
+// Packed layout, every symbol has a code: the tiled symbol-parallel kernel.
+int encode_tiled_on_device(aws_huffman_batch_ctx *ctx, const hb::BatchView &v, uint64_t total_in, cudaStream_t stream) {
+    const uint64_t num_tiles = (total_in + kEncTile - 1) / kEncTile;
+    const bool seg = v.n > 1;
+    const size_t state_bytes = num_tiles * sizeof(uint64_t) + 256;
+    HB_CUDA_TRY(ctx->tile_state.reserve(state_bytes));
+    HB_CUDA_TRY(cudaMemsetAsync(ctx->tile_state.ptr, 0, state_bytes, stream));
+    EncTiledArgs a{};
+    a.in = v.in;
+    a.in_offsets = v.in_offsets;
+    a.n = v.n;
+    a.total_in = total_in;
+    a.out = v.out;
+    a.out_capacity = v.out_capacity;
+    a.out_offsets = v.out_offsets;
+    a.tile_state = ctx->tile_state.as<uint64_t>();
+    a.ticket = reinterpret_cast<uint32_t *>(a.tile_state + num_tiles);
+    a.num_tiles = (uint32_t)num_tiles;
+    a.eos_padding = ctx->tables.eos_padding;
+    if (seg) {
+        HB_CUDA_TRY(ctx->tile_first.reserve((num_tiles + 1) * sizeof(uint32_t)));
+        a.tile_first = ctx->tile_first.as<uint32_t>();
+        tile_index_kernel<<<(unsigned)((num_tiles + 1 + 255) / 256), 256, 0, stream>>>(
+            v.in_offsets, v.n, total_in, num_tiles, ctx->tile_first.as<uint32_t>());
+        ++ctx->launches;
+        encode_tiled_kernel<true><<<(unsigned)num_tiles, kEncThreads, 0, stream>>>(ctx->tables.enc, a);
+    } else {
+        encode_tiled_kernel<false><<<(unsigned)num_tiles, kEncThreads, 0, stream>>>(ctx->tables.enc, a);
+    }
+    ++ctx->launches;
+    HB_CUDA_TRY(cudaGetLastError());
+    if (v.out_lens || v.status || v.consumed || v.overflow_pattern || v.overflow_num_bits) {
+        fill_packed_meta_kernel<<<(unsigned)((v.n + 255) / 256), 256, 0, stream>>>(
+            v.n, v.in_offsets, v.out_offsets, v.out_lens, v.status, v.consumed, v.overflow_pattern,
+            v.overflow_num_bits);
+        ++ctx->launches;
+        HB_CUDA_TRY(cudaGetLastError());
+    }
+    return AWS_OP_SUCCESS;
+}
+
+int encode_on_device(aws_huffman_batch_ctx *ctx, hb::BatchView v, uint64_t total_in, cudaStream_t stream) {
     if (v.n == 0) return AWS_OP_SUCCESS;
+    const bool force_generic = getenv("AWS_HUFFMAN_BATCH_FORCE_GENERIC") != nullptr;
+    if (!v.out_caps && !ctx->tables.has_unknown && total_in > 0 && v.n < 0xffffffffull &&
+        (total_in + kEncTile - 1) / kEncTile < 0xffffffffull && !force_generic) {
+        return encode_tiled_on_device(ctx, v, total_in, stream);
+    }
     if (!v.out_lens) {
         HB_CUDA_TRY(ctx->lens.reserve(v.n * sizeof(uint64_t)));
         v.out_lens = ctx->lens.as<uint64_t>();
@@ -228,9 +275,12 @@ int run_host_batch(aws_huffman_batch_ctx *ctx, const aws_huffman_batch *b, bool 
         v.leftover_num_bits = b->leftover_num_bits ? ctx->s_left_num.as<uint8_t>() : nullptr;
     }
 
-    if ((encode ? encode_on_device(ctx, v, st) : decode_on_device(ctx, v, st)) != AWS_OP_SUCCESS) return AWS_OP_ERR;
+    v.out_lens = b->out_lens ? ctx->lens.as<uint64_t>() : nullptr;
+    if ((encode ? encode_on_device(ctx, v, total_in, st) : decode_on_device(ctx, v, st)) != AWS_OP_SUCCESS)
+        return AWS_OP_ERR;
 
-    if (b->out_lens) HB_CUDA_TRY(cudaMemcpyAsync(b->out_lens, v.out_lens, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    if (b->out_lens)
+        HB_CUDA_TRY(cudaMemcpyAsync(b->out_lens, ctx->lens.ptr, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     if (b->status) HB_CUDA_TRY(cudaMemcpyAsync(b->status, v.status, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     if (b->consumed)
         HB_CUDA_TRY(cudaMemcpyAsync(b->consumed, v.consumed, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
@@ -380,7 +430,7 @@ void aws_huffman_batch_ctx_destroy(struct aws_huffman_batch_ctx *ctx) {
     }
     if (ctx->d_enc) cudaFree(ctx->d_enc);
     if (ctx->d_lut) cudaFree(ctx->d_lut);
-    GrowBuf *bufs[] = {&ctx->lens,     &ctx->tile_state, &ctx->s_in,       &ctx->s_in_off,      &ctx->s_out,
+    GrowBuf *bufs[] = {&ctx->lens,     &ctx->tile_state, &ctx->tile_first, &ctx->s_in,       &ctx->s_in_off,      &ctx->s_out,
                        &ctx->s_out_off, &ctx->s_caps,     &ctx->s_status,   &ctx->s_consumed,    &ctx->s_ovf_pattern,
                        &ctx->s_ovf_bits, &ctx->s_left_bits, &ctx->s_left_num};
     for (GrowBuf *g : bufs) g->release();
@@ -404,7 +454,7 @@ int aws_huffman_encode_batch_device(
     if (check_batch(batch)) return AWS_OP_ERR;
     HB_CUDA_TRY(cudaSetDevice(ctx->device));
     cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
-    return encode_on_device(ctx, make_view(batch), st);
+    return encode_on_device(ctx, make_view(batch), batch->in_size, st);
 }
 
 int aws_huffman_decode_batch_device(

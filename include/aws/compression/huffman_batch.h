@@ -45,7 +45,9 @@ struct aws_huffman_batch_ctx;
 struct aws_huffman_batch {
     size_t n;
     const uint8_t *in;
-    const uint64_t *in_offsets; /* n + 1 entries, non-decreasing */
+    const uint64_t *in_offsets; /* n + 1 entries, non-decreasing, in_offsets[0] == 0 */
+    uint64_t in_size;           /* == in_offsets[n]. The *_device entry points size their grids from it
+                                 * (in_offsets lives on the device there); the host entry points ignore it. */
 
     uint8_t *out;
     uint64_t out_capacity;   /* bytes addressable at `out` */

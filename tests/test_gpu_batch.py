@@ -248,3 +248,103 @@ def test_empty_batches_and_empty_items(contexts):
     assert not r["out_lens"].any() and not r["status"].any() and not r["out_offsets"].any()
     r = ctx.decode(np.zeros(0, dtype=np.uint8), np.zeros(6, dtype=np.uint64), 16)
     assert not r["out_lens"].any() and not r["status"].any()
+
+
+# ---- shapes that stress the tiled encoder: tile-straddling items, empties, 1-byte items, one long stream ----
+
+def _check_packed_encode_and_roundtrip(ctx, oracle, table, data, offs, eos=0xFF):
+    cap_total = 4 * len(data) + 64
+    want = oracle.encode_batch(table, eos, data, offs, cap_total)
+    got = ctx.encode(data, offs, cap_total)
+    assert_same_packed(got, want)
+    stream = want["out"][:int(want["out_offsets"][-1])]
+    want_d = oracle.decode_batch(table, stream, want["out_offsets"], len(data) + 64)
+    got_d = ctx.decode(stream, want["out_offsets"], len(data) + 64)
+    assert_same_packed(got_d, want_d)
+    return want
+
+
+@pytest.mark.parametrize("table_name", ["test", "hpack"])
+def test_ragged_item_shapes(contexts, oracle, oracle_tables, table_name):
+    rng = np.random.default_rng(0x7117)
+    ctx, table = contexts(table_name), oracle_tables[table_name]
+    shapes = {
+        "mixed": np.concatenate([rng.integers(0, 40, 3000), [4096, 4095, 4097, 1, 0, 0, 12289, 16, 15, 17],
+                                 rng.integers(0, 9000, 40), np.zeros(50, dtype=np.int64), [1] * 300, [0, 0, 0]]),
+        "all_empty_but_one": np.concatenate([np.zeros(500, dtype=np.int64), [7], np.zeros(500, dtype=np.int64)]),
+        "single_bytes": np.ones(9000, dtype=np.int64),
+        "tile_multiples": np.array([4096, 8192, 4096, 0, 4096], dtype=np.int64),
+        "one_item_exact_tile": np.array([4096], dtype=np.int64),
+        "two_items": np.array([5000, 3], dtype=np.int64),
+    }
+    for name, lens in shapes.items():
+        lens = np.asarray(lens, dtype=np.int64)
+        if name == "mixed":
+            lens = lens[rng.permutation(len(lens))]
+        offs = np.zeros(len(lens) + 1, dtype=np.uint64)
+        offs[1:] = np.cumsum(lens)
+        for zipf in (True, False):
+            if zipf:
+                data = refcodec.zipf_symbol_sampler(refcodec.table_arrays(table_name)[1])[
+                    rng.integers(0, 65536, size=int(offs[-1]))]
+            else:
+                data = rng.integers(0, 256, size=int(offs[-1]), dtype=np.uint8)
+            _check_packed_encode_and_roundtrip(ctx, oracle, table, np.ascontiguousarray(data), offs)
+
+
+@pytest.mark.parametrize("table_name", ["test", "hpack"])
+@pytest.mark.parametrize("nbytes", [1, 15, 16, 17, 4095, 4096, 4097, 1 << 20, (3 << 20) + 5])
+def test_single_stream(contexts, oracle, oracle_tables, table_name, nbytes):
+    """n == 1: the long-stream path (BASELINE configs 3/4 at a size the oracle finishes quickly)."""
+    rng = np.random.default_rng(nbytes)
+    ctx, table = contexts(table_name, 0x5A), oracle_tables[table_name]
+    sampler = refcodec.zipf_symbol_sampler(refcodec.table_arrays(table_name)[1])
+    data = np.ascontiguousarray(sampler[rng.integers(0, 65536, size=nbytes)])
+    offs = np.array([0, nbytes], dtype=np.uint64)
+    _check_packed_encode_and_roundtrip(ctx, oracle, table, data, offs, eos=0x5A)
+
+
+def test_worst_case_expansion(contexts, oracle, oracle_tables):
+    """All-longest-code input (30-bit HPACK codes, 3.75x expansion) and all-shortest-code input."""
+    ctx, table = contexts("hpack"), oracle_tables["hpack"]
+    for sym, n in ((10, 20000), (ord("0"), 20000), (22, 4096 * 3 + 1)):
+        data = np.full(n, sym, dtype=np.uint8)
+        for offs in (np.array([0, n], dtype=np.uint64), np.arange(0, n + 1, 1, dtype=np.uint64)[::7].copy()):
+            offs = np.ascontiguousarray(np.append(offs[offs < n], n).astype(np.uint64))
+            _check_packed_encode_and_roundtrip(ctx, oracle, table, data, offs)
+
+
+def test_device_pointer_entry_points(contexts, oracle, oracle_tables):
+    """aws_huffman_*_batch_device on torch CUDA tensors, including a misaligned input pointer."""
+    import torch
+    ctx, table = contexts("hpack"), oracle_tables["hpack"]
+    rng = np.random.default_rng(77)
+    data, offs = refcodec.random_batch(rng, 30000, 0, 200, "hpack")
+    want = oracle.encode_batch(table, 0xFF, data, offs, 4 * len(data) + 64)
+    total = int(want["out_offsets"][-1])
+    dev = torch.device("cuda", 0)
+    n = len(offs) - 1
+    for shift in (0, 3):
+        raw = torch.zeros(len(data) + 16, dtype=torch.uint8, device=dev)
+        raw[shift:shift + len(data)] = torch.from_numpy(data).to(dev)
+        d_in = raw[shift:shift + len(data)]
+        d_off = torch.from_numpy(offs.view(np.int64)).to(dev)
+        out_buf = torch.zeros(4 * len(data) + 64 + 16, dtype=torch.uint8, device=dev)
+        d_out = out_buf[shift:]
+        d_out_off = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+        d_lens = torch.zeros(n, dtype=torch.int64, device=dev)
+        st = torch.cuda.Stream(dev)
+        with torch.cuda.stream(st):
+            ctx.encode_device(n, {"in_": d_in, "in_offsets": d_off, "out": d_out, "out_offsets": d_out_off,
+                                  "out_lens": d_lens}, len(data), 4 * len(data) + 64, stream=st.cuda_stream)
+            st.synchronize()
+            assert np.array_equal(d_out_off.cpu().numpy().view(np.uint64), want["out_offsets"])
+            assert np.array_equal(d_out[:total].cpu().numpy(), want["out"][:total])
+            assert np.array_equal(d_lens.cpu().numpy().view(np.uint64), want["out_lens"])
+            back = torch.zeros(len(data) + 64, dtype=torch.uint8, device=dev)
+            back_off = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+            ctx.decode_device(n, {"in_": d_out, "in_offsets": d_out_off, "out": back, "out_offsets": back_off},
+                              total, len(data) + 64, stream=st.cuda_stream)
+            st.synchronize()
+            assert np.array_equal(back[:len(data)].cpu().numpy(), data)
+            assert np.array_equal(back_off.cpu().numpy().view(np.uint64), offs)
