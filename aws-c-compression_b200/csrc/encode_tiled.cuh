@@ -8,11 +8,16 @@
 //      reduces them to a "segment function"  p -> p + head            (no item starts in its range)
 //                                            p -> ceil8(p + head) + tail   (items start in its range;
 //      an item start byte-aligns the output because the previous item is padded, huffman.c:178-184)
-//   B. warp-shuffle scan + block scan of those functions; one warp runs a single-pass decoupled
-//      look-back over tile descriptors to get the absolute output bit position G of the tile
-//   C. each thread re-reads its codes and packs them MSB-first into a shared-memory staging buffer
-//      at its exact bit position with a 64-bit funnel accumulator; words shared with a neighbour are
-//      merged with shared-memory atomicOr, interior words are plain stores
+//   B. warp-shuffle scan + block scan of those functions. The tile's own function is published to its
+//      look-back descriptor immediately (before the expensive packing) so that successors rarely wait;
+//      after packing one warp resolves the absolute output bit position G of the tile (single-pass
+//      decoupled look-back)
+//      (A is done while packing: each thread packs its 16 codes MSB-first, left-aligned, into a private
+//      bank-conflict-free shared-memory slot with a 64-bit funnel accumulator and a branch-free,
+//      predicated word flush; the bit count of that packing is the function's operand)
+//   C. once positions are known each thread shift-copies its packed words to their exact bit position
+//      in the tile's staging buffer: interior words are plain stores, the first and last word of a run
+//      (shared with a neighbour) are merged with shared-memory atomicOr
 //   D. the staged bytes this tile owns (those whose first bit lies in the tile) are copied to global
 //      memory with 128-bit stores. The bits that complete the tile's last byte belong to the next
 //      tile's first symbols (or to the EOS padding); one thread recomputes them from the input, so
@@ -78,53 +83,60 @@ __device__ __forceinline__ uint64_t seg_pack_aggregate(const Seg &f) {
     return (kLbAggregate << kLbFlagShift) | ((uint64_t)f.hb << 61) | ((uint64_t)f.head << 31) | (uint64_t)f.tail;
 }
 
-// One full warp. Publishes the tile's function, resolves the absolute start position G of the tile by
-// walking back to the nearest tile whose end position is known, publishes this tile's end position.
-__device__ __forceinline__ uint64_t seg_lookback(uint64_t *tile_state, uint32_t tile, const Seg &agg) {
+// Lane 0 of any warp: make this tile's own function visible as early as possible.
+__device__ __forceinline__ void seg_publish_aggregate(uint64_t *tile_state, uint32_t tile, const Seg &agg) {
+    if (tile == 0)
+        st_relaxed_u64(&tile_state[0], (kLbPrefix << kLbFlagShift) | (seg_apply(agg, 0) & kLbValueMask));
+    else
+        st_relaxed_u64(&tile_state[tile], seg_pack_aggregate(agg));
+}
+
+// One full warp, some time after seg_publish_aggregate. Resolves the absolute start position G of the
+// tile by walking back to the nearest tile whose end position is known, then publishes this tile's
+// end position.
+__device__ __forceinline__ uint64_t seg_resolve(uint64_t *tile_state, uint32_t tile, const Seg &agg) {
     const uint32_t lane = lane_id();
+    if (tile == 0) return 0;
     uint64_t G = 0;
-    if (tile != 0) {
-        if (lane == 0) st_relaxed_u64(&tile_state[tile], seg_pack_aggregate(agg));
-        Seg64 acc = {0, 0, 0};  // function of tiles (look+1 .. tile-1), identity so far
-        int64_t look = (int64_t)tile - 1;
-        while (true) {
-            const int64_t idx = look - (int64_t)lane;
-            uint64_t word = kLbPrefix << kLbFlagShift;  // "tile -1" ends at bit 0
-            if (idx >= 0) {
-                do {
-                    word = ld_relaxed_u64(&tile_state[idx]);
-                } while ((word >> kLbFlagShift) == kLbInvalid);
-            }
-            const bool is_prefix = (word >> kLbFlagShift) == kLbPrefix;
-            const uint32_t pmask = __ballot_sync(0xffffffffu, is_prefix);
-            const uint32_t first = pmask ? (uint32_t)(__ffs(pmask) - 1) : 32u;
-            Seg64 f = {0, 0, 0};
-            if (lane < first) {
-                f.hb = (uint32_t)(word >> 61) & 1u;
-                f.head = (word >> 31) & 0x3FFFFFFFull;
-                f.tail = word & 0x7FFFFFFFull;
-            }
-            // ordered reduction: higher lanes hold EARLIER tiles
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                Seg64 o;
-                o.head = __shfl_down_sync(0xffffffffu, f.head, d);
-                o.tail = __shfl_down_sync(0xffffffffu, f.tail, d);
-                o.hb = __shfl_down_sync(0xffffffffu, f.hb, d);
-                if (lane + d < 32) f = seg_combine64(o, f);
-            }
-            Seg64 window;
-            window.head = __shfl_sync(0xffffffffu, f.head, 0);
-            window.tail = __shfl_sync(0xffffffffu, f.tail, 0);
-            window.hb = __shfl_sync(0xffffffffu, f.hb, 0);
-            acc = seg_combine64(window, acc);
-            if (pmask) {
-                const uint64_t end_of_known = __shfl_sync(0xffffffffu, word & kLbValueMask, first);
-                G = seg_apply64(acc, end_of_known);
-                break;
-            }
-            look -= 32;
+    Seg64 acc = {0, 0, 0};  // function of tiles (look+1 .. tile-1), identity so far
+    int64_t look = (int64_t)tile - 1;
+    while (true) {
+        const int64_t idx = look - (int64_t)lane;
+        uint64_t word = kLbPrefix << kLbFlagShift;  // "tile -1" ends at bit 0
+        if (idx >= 0) {
+            do {
+                word = ld_relaxed_u64(&tile_state[idx]);
+            } while ((word >> kLbFlagShift) == kLbInvalid);
         }
+        const bool is_prefix = (word >> kLbFlagShift) == kLbPrefix;
+        const uint32_t pmask = __ballot_sync(0xffffffffu, is_prefix);
+        const uint32_t first = pmask ? (uint32_t)(__ffs(pmask) - 1) : 32u;
+        Seg64 f = {0, 0, 0};
+        if (lane < first) {
+            f.hb = (uint32_t)(word >> 61) & 1u;
+            f.head = (word >> 31) & 0x3FFFFFFFull;
+            f.tail = word & 0x7FFFFFFFull;
+        }
+        // ordered reduction: higher lanes hold EARLIER tiles
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            Seg64 o;
+            o.head = __shfl_down_sync(0xffffffffu, f.head, d);
+            o.tail = __shfl_down_sync(0xffffffffu, f.tail, d);
+            o.hb = __shfl_down_sync(0xffffffffu, f.hb, d);
+            if (lane + d < 32) f = seg_combine64(o, f);
+        }
+        Seg64 window;
+        window.head = __shfl_sync(0xffffffffu, f.head, 0);
+        window.tail = __shfl_sync(0xffffffffu, f.tail, 0);
+        window.hb = __shfl_sync(0xffffffffu, f.hb, 0);
+        acc = seg_combine64(window, acc);
+        if (pmask) {
+            const uint64_t end_of_known = __shfl_sync(0xffffffffu, word & kLbValueMask, first);
+            G = seg_apply64(acc, end_of_known);
+            break;
+        }
+        look -= 32;
     }
     if (lane == 0) st_relaxed_u64(&tile_state[tile], (kLbPrefix << kLbFlagShift) | (seg_apply(agg, G) & kLbValueMask));
     return G;
@@ -160,41 +172,40 @@ struct EncTiledArgs {
     uint32_t eos_padding;
 };
 
-template <bool kSeg>
-__global__ void __launch_bounds__(kEncThreads) encode_tiled_kernel(const uint2 *__restrict__ enc_table, EncTiledArgs a) {
-    __shared__ uint2 s_tab[256];
-    __shared__ uint32_t s_mask[kEncTile / 32];
-    __shared__ uint32_t s_first_item[kEncThreads];
-    __shared__ Seg s_warp[kEncThreads / 32];
-    __shared__ uint32_t s_tile;
-    __shared__ uint64_t s_G, s_Gend;
-    __shared__ __align__(16) uint32_t s_stage[kEncStageBytes / 4];
+// Appends one code to a right-aligned 64-bit accumulator; whenever 32 bits are complete they go to the
+// thread's private slot (row-interleaved: word j of thread t at s_slot[j * kEncThreads + t], so lanes
+// never collide on a bank). `nbm` = bits in acc minus 32, so "a word is ready" is nbm >= 0 and the
+// wrap-around after a flush is a single OR. No branches: the store and pointer bump are predicated.
+#define HB_ENC_APPEND(code_, len_)                                                                                     \
+    do {                                                                                                               \
+        acc = (acc << (len_)) | (uint64_t)(code_);                                                                     \
+        nbm += (int)(len_);                                                                                            \
+        const bool full_ = nbm >= 0;                                                                                   \
+        const uint32_t word_ = __funnelshift_r((uint32_t)acc, (uint32_t)(acc >> 32), (uint32_t)nbm);                   \
+        if (full_) *sp = word_;                                                                                        \
+        sp += full_ ? kEncThreads : 0;                                                                                 \
+        nbm |= ~31;                                                                                                    \
+    } while (0)
+
+// kSeg : items may start inside the tile (n > 1)
+// kFull: the tile holds exactly kEncTile symbols (everything but the last tile of the input)
+template <bool kSeg, bool kFull>
+__device__ __forceinline__ void encode_tile(
+    const uint2 *__restrict__ enc_table, const EncTiledArgs &a, uint32_t tile, uint2 *s_tab, uint32_t *s_mask,
+    uint32_t *s_first_item, Seg *s_warp, uint64_t *s_pos, uint32_t *s_slot, uint16_t *s_runbits, uint32_t *s_stage) {
 
     const uint32_t tid = threadIdx.x;
     const uint32_t lane = tid & 31, warp = tid >> 5;
-
-    if (tid == 0) s_tile = atomicAdd(a.ticket, 1u);
-    s_tab[tid] = enc_table[tid];
-    if (kSeg) {
-        if (tid < kEncTile / 32) s_mask[tid] = 0;
-        s_first_item[tid] = 0xffffffffu;
-    }
-    {
-        uint4 *z = reinterpret_cast<uint4 *>(s_stage);
-        for (uint32_t i = tid; i < kEncStageBytes / 16; i += kEncThreads) z[i] = make_uint4(0, 0, 0, 0);
-    }
-    __syncthreads();
-
-    const uint32_t tile = s_tile;
     const uint64_t t0 = (uint64_t)tile * kEncTile;
-    const uint64_t t1 = min(t0 + (uint64_t)kEncTile, a.total_in);
+    const uint64_t t1 = kFull ? t0 + kEncTile : a.total_in;
     const uint64_t p0 = t0 + (uint64_t)tid * kEncSymsPerThread;
-    const uint32_t nsym = p0 >= t1 ? 0u : (uint32_t)min((uint64_t)kEncSymsPerThread, t1 - p0);
+    const uint32_t nsym = kFull ? (uint32_t)kEncSymsPerThread
+                                : (p0 >= t1 ? 0u : (uint32_t)min((uint64_t)kEncSymsPerThread, t1 - p0));
 
     // ---- load 16 symbols -------------------------------------------------------------------------
     uint32_t w[4] = {0, 0, 0, 0};
     if (nsym == kEncSymsPerThread && ((reinterpret_cast<uintptr_t>(a.in) & 15) == 0)) {
-        const uint4 v = *reinterpret_cast<const uint4 *>(a.in + p0);
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(a.in + p0));
         w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
     } else {
 #pragma unroll
@@ -203,9 +214,10 @@ __global__ void __launch_bounds__(kEncThreads) encode_tiled_kernel(const uint2 *
     }
 
     // ---- item starts inside the tile ------------------------------------------------------------------
-    uint32_t first_in_tile = 0, end_in_tile = 0;
+    uint32_t end_in_tile = 0;
+    uint32_t m = 0;
     if (kSeg) {
-        first_in_tile = a.tile_first[tile];
+        const uint32_t first_in_tile = a.tile_first[tile];
         end_in_tile = a.tile_first[tile + 1];
         for (uint32_t i = first_in_tile + tid; i < end_in_tile; i += kEncThreads) {
             const uint32_t p = (uint32_t)(a.in_offsets[i] - t0);
@@ -213,27 +225,28 @@ __global__ void __launch_bounds__(kEncThreads) encode_tiled_kernel(const uint2 *
             atomicMin(&s_first_item[p >> 4], i);
         }
         __syncthreads();
+        m = (s_mask[tid >> 1] >> ((tid & 1) * 16)) & 0xffffu;
     }
-    const uint32_t m = kSeg ? ((s_mask[tid >> 1] >> ((tid & 1) * 16)) & 0xffffu) : 0u;
 
-    // ---- A: the thread's segment function -------------------------------------------------------------
+    // ---- A: code lengths only -> my segment function (cheap; lets the tile publish early) ---------------
     Seg mine = {0, 0, 0};
+    {
+        uint32_t run = 0;
 #pragma unroll
-    for (int k = 0; k < kEncSymsPerThread; ++k) {
-        const uint32_t sym = (w[k >> 2] >> (8 * (k & 3))) & 0xffu;
-        const uint32_t len = (uint32_t)k < nsym ? s_tab[sym].y : 0u;
-        if (kSeg) {
-            if ((m >> k) & 1u) {
-                if (mine.hb) mine.tail = (mine.tail + 7u) & ~7u;
+        for (int k = 0; k < kEncSymsPerThread; ++k) {
+            if (!kFull && (uint32_t)k >= nsym) break;
+            if (kSeg && ((m >> k) & 1u)) {
+                if (mine.hb) mine.tail += (run + 7u) & ~7u; else mine.head = run;
                 mine.hb = 1;
+                run = 0;
             }
-            if (mine.hb) mine.tail += len; else mine.head += len;
-        } else {
-            mine.head += len;
+            const uint32_t sym = (w[k >> 2] >> (8 * (k & 3))) & 0xffu;
+            run += s_tab[sym].y;
         }
+        if (mine.hb) mine.tail += run; else mine.head = run;
     }
 
-    // ---- B: block scan of functions + look-back -----------------------------------------------------
+    // ---- B: block scan of segment functions; publish the tile's function right away -----------------------
     Seg incl = mine;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -244,7 +257,9 @@ __global__ void __launch_bounds__(kEncThreads) encode_tiled_kernel(const uint2 *
     if (lane == 0) excl = Seg{0, 0, 0};
     if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
-    if (warp == 0) {
+    Seg total;
+    {
+        // every warp redoes the 8-entry scan (cheaper than another barrier)
         Seg wv = lane < kEncThreads / 32 ? s_warp[lane] : Seg{0, 0, 0};
         Seg wi = wv;
 #pragma unroll
@@ -254,73 +269,114 @@ __global__ void __launch_bounds__(kEncThreads) encode_tiled_kernel(const uint2 *
         }
         Seg we = seg_shfl_up(wi, 1);
         if (lane == 0) we = Seg{0, 0, 0};
-        Seg total;
         total.head = __shfl_sync(0xffffffffu, wi.head, kEncThreads / 32 - 1);
         total.tail = __shfl_sync(0xffffffffu, wi.tail, kEncThreads / 32 - 1);
         total.hb = __shfl_sync(0xffffffffu, wi.hb, kEncThreads / 32 - 1);
-        if (lane < kEncThreads / 32) s_warp[lane] = we;  // exclusive per-warp functions
-        const uint64_t G = seg_lookback(a.tile_state, tile, total);
+        Seg mywarp;
+        mywarp.head = __shfl_sync(0xffffffffu, we.head, warp);
+        mywarp.tail = __shfl_sync(0xffffffffu, we.tail, warp);
+        mywarp.hb = __shfl_sync(0xffffffffu, we.hb, warp);
+        excl = seg_combine(mywarp, excl);  // my exclusive function from the start of the tile
+    }
+    if (tid == 0) seg_publish_aggregate(a.tile_state, tile, total);
+
+    // ---- C: pack my symbols into my private slot, run by run (position independent) ------------------------
+    // A "run" is a maximal stretch of my symbols inside one item. Runs are packed left-aligned, each
+    // starting on a fresh slot word; finished runs leave their bit count in s_runbits[run][tid].
+    uint64_t acc = 0;
+    int nbm = -32;
+    uint32_t *sp = s_slot + tid;
+    uint32_t *run_begin = sp;
+    uint32_t runs_done = 0;
+#pragma unroll
+    for (int k = 0; k < kEncSymsPerThread; ++k) {
+        if (!kFull && (uint32_t)k >= nsym) break;
+        if (kSeg && ((m >> k) & 1u)) {
+            // an item starts at symbol k: close the current run
+            const uint32_t rem = (uint32_t)(nbm + 32);
+            const uint32_t bits = (uint32_t)(sp - run_begin) / kEncThreads * 32u + rem;
+            if (rem) {
+                *sp = (uint32_t)(acc << (32 - rem));
+                sp += kEncThreads;
+            }
+            s_runbits[runs_done * kEncThreads + tid] = (uint16_t)bits;
+            ++runs_done;
+            run_begin = sp;
+            acc = 0;
+            nbm = -32;
+        }
+        const uint32_t sym = (w[k >> 2] >> (8 * (k & 3))) & 0xffu;
+        const uint2 e = s_tab[sym];
+        HB_ENC_APPEND(e.x, e.y);
+    }
+    uint32_t last_bits;
+    {
+        const uint32_t rem = (uint32_t)(nbm + 32);
+        last_bits = (uint32_t)(sp - run_begin) / kEncThreads * 32u + rem;
+        if (rem) *sp = (uint32_t)(acc << (32 - rem));
+    }
+
+    // ---- D: resolve the tile's absolute position (predecessors published long ago) -------------------------
+    if (warp == 0) {
+        const uint64_t G0 = seg_resolve(a.tile_state, tile, total);
         if (lane == 0) {
-            s_G = G;
-            s_Gend = seg_apply(total, G);
+            s_pos[0] = G0;
+            s_pos[1] = seg_apply(total, G0);
         }
     }
     __syncthreads();
 
-    const uint64_t G = s_G, Gend = s_Gend;
-    const uint64_t P = seg_apply(excl, seg_apply(s_warp[warp], G));  // absolute bit position of my first code
+    const uint64_t G = s_pos[0], Gend = s_pos[1];
+    const uint64_t P = seg_apply(excl, G);  // absolute bit position of my first code
 
     // Staging origin: stage byte 0 <-> global address (out + G/8) rounded down to 16 bytes.
     const uint64_t g_byte0 = G >> 3;
     const uint32_t misalign = (uint32_t)((reinterpret_cast<uintptr_t>(a.out) + g_byte0) & 15);
     const int64_t origin_byte = (int64_t)g_byte0 - (int64_t)misalign;  // absolute output byte of stage byte 0
 
-    // ---- C: pack my codes into the stage --------------------------------------------------------------
+    // ---- 3: shift-copy my runs from the slot to their bit positions in the stage ------------------------------
     {
-        const uint32_t q = (uint32_t)((int64_t)P - origin_byte * 8);  // stage bit index of my first bit
-        uint32_t widx = q >> 5;
-        uint32_t nb = q & 31;          // bits in acc, counting the phantom bits of the shared first word
-        uint64_t acc = 0;
-        bool shared_word = nb != 0;    // my first word also holds a neighbour's bits
+        uint32_t D = (uint32_t)((int64_t)P - origin_byte * 8);  // stage bit index of the current run
+        const uint32_t *src = s_slot + tid;
         uint32_t cur_item = kSeg ? s_first_item[tid] : 0u;
-
-        auto append = [&](uint32_t code, uint32_t len) {
-            acc = (acc << len) | code;
-            nb += len;
-            if (nb >= 32) {
-                nb -= 32;
-                const uint32_t word = __byte_perm((uint32_t)(acc >> nb), 0, 0x0123);  // stream order in memory
-                if (shared_word) {
-                    atomicOr(&s_stage[widx], word);
-                    shared_word = false;
-                } else {
-                    s_stage[widx] = word;
+        uint32_t boundary_bits = m;
+        const uint32_t num_runs = runs_done + 1;
+        for (uint32_t r = 0; r < num_runs; ++r) {
+            const uint32_t bits = (r + 1 == num_runs) ? last_bits : (uint32_t)s_runbits[r * kEncThreads + tid];
+            if (kSeg && r > 0) {
+                // byte-align: pad the item that just ended with the LOW bits of eos_padding
+                // (reference huffman.c:178-184), then note where the new item starts
+                const uint32_t pad = (8u - (D & 7u)) & 7u;
+                if (pad) {
+                    const uint32_t v = a.eos_padding & ((1u << pad) - 1u);
+                    atomicOr(&s_stage[D >> 5], __byte_perm(v << (32 - (D & 31) - pad), 0, 0x0123));
+                    D += pad;
                 }
-                ++widx;
+                const uint32_t k = (uint32_t)__ffs(boundary_bits) - 1;
+                boundary_bits &= boundary_bits - 1;
+                const uint64_t here = p0 + k;
+                const uint64_t ob = (uint64_t)(origin_byte + (int64_t)(D >> 3));
+                do {
+                    a.out_offsets[cur_item] = ob;
+                    ++cur_item;
+                } while (cur_item < a.n && a.in_offsets[cur_item] == here);
             }
-        };
-
-#pragma unroll
-        for (int k = 0; k < kEncSymsPerThread; ++k) {
-            if ((uint32_t)k < nsym) {
-                if (kSeg && ((m >> k) & 1u)) {
-                    // an item starts here: pad the previous one to a byte boundary, then record where
-                    // this item (and any empty items sharing its start) begins in the output
-                    const uint32_t pad = (8u - (nb & 7u)) & 7u;
-                    if (pad) append(a.eos_padding & ((1u << pad) - 1u), pad);
-                    const uint64_t ob = (uint64_t)(origin_byte + (int64_t)(((uint64_t)widx * 32 + nb) >> 3));
-                    const uint64_t here = p0 + k;
-                    do {
-                        a.out_offsets[cur_item] = ob;
-                        ++cur_item;
-                    } while (cur_item < a.n && a.in_offsets[cur_item] == here);
+            if (bits) {
+                const uint32_t sh = D & 31;
+                uint32_t *dst = s_stage + (D >> 5);
+                const uint32_t nsrc = (bits + 31) >> 5;
+                const uint32_t ndst = (sh + bits + 31) >> 5;
+                uint32_t prev = 0;
+                for (uint32_t j = 0; j < ndst; ++j) {
+                    const uint32_t cur = j < nsrc ? src[j * kEncThreads] : 0u;
+                    const uint32_t word = __byte_perm(__funnelshift_r(cur, prev, sh), 0, 0x0123);
+                    if (j == 0 || j + 1 == ndst) atomicOr(dst + j, word); else dst[j] = word;
+                    prev = cur;
                 }
-                const uint32_t sym = (w[k >> 2] >> (8 * (k & 3))) & 0xffu;
-                const uint2 e = s_tab[sym];
-                append(e.x, e.y);
+                src += nsrc * kEncThreads;
+                D += bits;
             }
         }
-        if (nb) atomicOr(&s_stage[widx], __byte_perm((uint32_t)(acc << (32 - nb)), 0, 0x0123));
     }
 
     // ---- the bits that complete this tile's last byte ------------------------------------------------
@@ -356,7 +412,7 @@ __global__ void __launch_bounds__(kEncThreads) encode_tiled_kernel(const uint2 *
     }
     __syncthreads();
 
-    // ---- D: copy the bytes this tile owns ------------------------------------------------------------------
+    // ---- 4: copy the bytes this tile owns ------------------------------------------------------------------
     {
         const uint64_t own_lo = (G + 7) >> 3, own_hi = min((Gend + 7) >> 3, a.out_capacity);
         if (own_hi > own_lo) {
@@ -376,6 +432,42 @@ __global__ void __launch_bounds__(kEncThreads) encode_tiled_kernel(const uint2 *
             }
         }
     }
+}
+
+constexpr int kEncSlotWords = kEncTile;  // 16 words per thread: every symbol fits one word
+constexpr size_t kEncSmemBytes = kEncSlotWords * 4 + kEncStageBytes + kEncTile * 2 /* runbits */;
+
+template <bool kSeg>
+__global__ void __launch_bounds__(kEncThreads, 4) encode_tiled_kernel(const uint2 *__restrict__ enc_table, EncTiledArgs a) {
+    __shared__ uint2 s_tab[256];
+    __shared__ uint32_t s_mask[kEncTile / 32];
+    __shared__ uint32_t s_first_item[kEncThreads];
+    __shared__ Seg s_warp[kEncThreads / 32];
+    __shared__ uint32_t s_tile;
+    __shared__ uint64_t s_pos[2];
+    extern __shared__ __align__(16) uint8_t s_dyn[];
+    uint32_t *s_stage = reinterpret_cast<uint32_t *>(s_dyn);
+    uint32_t *s_slot = reinterpret_cast<uint32_t *>(s_dyn + kEncStageBytes);
+    uint16_t *s_runbits = reinterpret_cast<uint16_t *>(s_dyn + kEncStageBytes + kEncSlotWords * 4);
+
+    const uint32_t tid = threadIdx.x;
+    if (tid == 0) s_tile = atomicAdd(a.ticket, 1u);
+    s_tab[tid] = enc_table[tid];
+    if (kSeg) {
+        if (tid < kEncTile / 32) s_mask[tid] = 0;
+        s_first_item[tid] = 0xffffffffu;
+    }
+    {
+        uint4 *z = reinterpret_cast<uint4 *>(s_stage);
+        for (uint32_t i = tid; i < kEncStageBytes / 16; i += kEncThreads) z[i] = make_uint4(0, 0, 0, 0);
+    }
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const bool full = (uint64_t)(tile + 1) * kEncTile <= a.total_in;
+    if (full)
+        encode_tile<kSeg, true>(enc_table, a, tile, s_tab, s_mask, s_first_item, s_warp, s_pos, s_slot, s_runbits, s_stage);
+    else
+        encode_tile<kSeg, false>(enc_table, a, tile, s_tab, s_mask, s_first_item, s_warp, s_pos, s_slot, s_runbits, s_stage);
 }
 
 // Optional per-item arrays in the packed layout when no symbol can be unknown: every item succeeds.

@@ -157,9 +157,9 @@ int encode_tiled_on_device(aws_huffman_batch_ctx *ctx, const hb::BatchView &v, u
         tile_index_kernel<<<(unsigned)((num_tiles + 1 + 255) / 256), 256, 0, stream>>>(
             v.in_offsets, v.n, total_in, num_tiles, ctx->tile_first.as<uint32_t>());
         ++ctx->launches;
-        encode_tiled_kernel<true><<<(unsigned)num_tiles, kEncThreads, 0, stream>>>(ctx->tables.enc, a);
+        encode_tiled_kernel<true><<<(unsigned)num_tiles, kEncThreads, kEncSmemBytes, stream>>>(ctx->tables.enc, a);
     } else {
-        encode_tiled_kernel<false><<<(unsigned)num_tiles, kEncThreads, 0, stream>>>(ctx->tables.enc, a);
+        encode_tiled_kernel<false><<<(unsigned)num_tiles, kEncThreads, kEncSmemBytes, stream>>>(ctx->tables.enc, a);
     }
     ++ctx->launches;
     HB_CUDA_TRY(cudaGetLastError());
