@@ -13,8 +13,9 @@ constexpr int32_t kStatusUnknownSymbol = 3072;  // AWS_ERROR_COMPRESSION_UNKNOWN
 
 constexpr uint64_t kNoCap = ~0ull;  // "all the room it needs" (packed layout)
 
-// Decode LUT entry layout: see host/huffman_lut.h.
-constexpr uint32_t kLutLeafFlag = 0x80000000u;
+// Device decode LUT entry (host/huffman_lut.h entries are re-encoded at context creation so the common
+// case needs one shift): leaf = len << 8 | symbol, link = 0x80000000 | width << 24 | base, hole = 0.
+constexpr uint32_t kDevLutLinkFlag = 0x80000000u;
 
 // Device-resident tables of one context. Pointers are device pointers.
 struct DeviceTables {

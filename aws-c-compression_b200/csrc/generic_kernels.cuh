@@ -178,10 +178,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) encode_items_warp_kernel(
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t lut_lookup(
     const uint32_t *s_lut, uint32_t s_count, const uint32_t *g_lut, uint32_t root_bits, uint32_t window) {
+    // device entry format: leaf = len << 8 | symbol, link = 0x80000000 | width << 24 | base, hole = 0
     uint32_t e = s_lut[window >> (32 - root_bits)];
     uint32_t used = root_bits;
-    while (e != 0 && !(e & kLutLeafFlag)) {
-        const uint32_t width = e >> 24;
+    while ((int32_t)e < 0) {
+        const uint32_t width = (e >> 24) & 0x7fu;
         const uint32_t idx = (e & 0xFFFFFFu) + ((window << used) >> (32 - width));
         e = idx < s_count ? s_lut[idx] : __ldg(&g_lut[idx]);
         used += width;
@@ -229,7 +230,7 @@ __global__ void __launch_bounds__(256) decode_items_thread_kernel(DeviceTables t
             if (bits_left >= 32) status = kStatusUnknownSymbol;
             break;
         }
-        const uint32_t used = (e >> 8) & 0x3Fu;
+        const uint32_t used = e >> 8;
         if (used > bits_left) break;
         if (out_len == C) {
             status = kStatusShortBuffer;

@@ -10,6 +10,7 @@
 #include "device_common.cuh"
 #include "generic_kernels.cuh"
 #include "encode_tiled.cuh"
+#include "decode_fast.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -80,7 +81,8 @@ struct aws_huffman_batch_ctx {
     uint64_t launches = 0;
 
     // scratch for the device entry points
-    GrowBuf lens, tile_state, tile_first;
+    GrowBuf lens, tile_state, tile_first, chunks, chunk_lens, chunk_offsets;
+    int sm_count = 148;
     // staging for the host entry points
     GrowBuf s_in, s_in_off, s_out, s_out_off, s_caps, s_status, s_consumed, s_ovf_pattern, s_ovf_bits, s_left_bits,
         s_left_num;
@@ -197,8 +199,71 @@ int encode_on_device(aws_huffman_batch_ctx *ctx, hb::BatchView v, uint64_t total
     return AWS_OP_SUCCESS;
 }
 
-int decode_on_device(aws_huffman_batch_ctx *ctx, hb::BatchView v, cudaStream_t stream) {
+// Packed layout, many strings: fused count -> look-back -> write kernel (one thread per string).
+int decode_batch_fast(aws_huffman_batch_ctx *ctx, const hb::BatchView &v, cudaStream_t stream) {
+    const uint64_t num_tiles = (v.n + kDecThreads - 1) / kDecThreads;
+    const size_t state_bytes = num_tiles * sizeof(uint64_t) + 256;
+    HB_CUDA_TRY(ctx->tile_state.reserve(state_bytes));
+    HB_CUDA_TRY(cudaMemsetAsync(ctx->tile_state.ptr, 0, state_bytes, stream));
+    DecBatchArgs a{};
+    a.b = v;
+    a.lut = ctx->tables.lut;
+    a.lut_count = ctx->tables.lut_count;
+    a.root_bits = ctx->tables.lut_root_bits;
+    a.tile_state = ctx->tile_state.as<uint64_t>();
+    a.ticket = reinterpret_cast<uint32_t *>(a.tile_state + num_tiles);
+    a.num_tiles = (uint32_t)num_tiles;
+    const unsigned blocks = (unsigned)std::min<uint64_t>(num_tiles, (uint64_t)ctx->sm_count * 12);
+    decode_batch_kernel<<<blocks, kDecThreads, ctx->tables.lut_count * sizeof(uint32_t), stream>>>(a);
+    ++ctx->launches;
+    HB_CUDA_TRY(cudaGetLastError());
+    return AWS_OP_SUCCESS;
+}
+
+// Packed layout, one long stream: chunked speculative decode.
+int decode_stream_fast(aws_huffman_batch_ctx *ctx, const hb::BatchView &v, uint64_t len, cudaStream_t stream) {
+    const uint64_t num_chunks = (len * 8 + kChunkBits - 1) / kChunkBits;
+    HB_CUDA_TRY(ctx->chunks.reserve(num_chunks * sizeof(uint64_t) + 64));
+    HB_CUDA_TRY(ctx->chunk_lens.reserve(num_chunks * sizeof(uint64_t)));
+    HB_CUDA_TRY(ctx->chunk_offsets.reserve((num_chunks + 1) * sizeof(uint64_t)));
+    StreamArgs a{};
+    a.in = v.in;
+    a.len = len;
+    a.num_chunks = num_chunks;
+    a.chunks = ctx->chunks.as<uint64_t>();
+    a.chunk_offsets = ctx->chunk_offsets.as<uint64_t>();
+    a.control = a.chunks + num_chunks;  // two words after the records
+    a.lut = ctx->tables.lut;
+    a.lut_count = ctx->tables.lut_count;
+    a.root_bits = ctx->tables.lut_root_bits;
+    HB_CUDA_TRY(cudaMemsetAsync(a.control, 0xff, 2 * sizeof(uint64_t), stream));
+    const size_t smem = ctx->tables.lut_count * sizeof(uint32_t);
+    const unsigned wide = (unsigned)std::min<uint64_t>((num_chunks + kStreamThreads - 1) / kStreamThreads,
+                                                       (uint64_t)ctx->sm_count * 12);
+    const unsigned flat = (unsigned)std::min<uint64_t>((num_chunks + 255) / 256, (uint64_t)ctx->sm_count * 8);
+    stream_sync_kernel<<<wide, kStreamThreads, smem, stream>>>(a);
+    for (int round = 0; round < 2; ++round) stream_fix_kernel<<<wide, kStreamThreads, smem, stream>>>(a);
+    stream_verify_kernel<<<flat, 256, 0, stream>>>(a);
+    stream_repair_kernel<<<1, 32, smem, stream>>>(a);
+    stream_counts_kernel<<<flat, 256, 0, stream>>>(a, ctx->chunk_lens.as<uint64_t>());
+    ctx->launches += 6;
+    HB_CUDA_TRY(cudaGetLastError());
+    if (launch_scan(ctx, ctx->chunk_lens.as<uint64_t>(), a.chunk_offsets, num_chunks, stream)) return AWS_OP_ERR;
+    stream_write_kernel<<<wide, kStreamThreads, smem, stream>>>(a, v);
+    ++ctx->launches;
+    HB_CUDA_TRY(cudaGetLastError());
+    return AWS_OP_SUCCESS;
+}
+
+constexpr uint64_t kStreamMinBytes = 64 * 1024;  // shorter single items go through the batch kernel
+
+int decode_on_device(aws_huffman_batch_ctx *ctx, hb::BatchView v, uint64_t total_in, cudaStream_t stream) {
     if (v.n == 0) return AWS_OP_SUCCESS;
+    const bool force_generic = getenv("AWS_HUFFMAN_BATCH_FORCE_GENERIC") != nullptr;
+    if (!v.out_caps && ctx->tables.lut_count <= kDecLutMaxSmem && !force_generic) {
+        if (v.n == 1 && total_in >= kStreamMinBytes) return decode_stream_fast(ctx, v, total_in, stream);
+        return decode_batch_fast(ctx, v, stream);
+    }
     if (!v.out_lens) {
         HB_CUDA_TRY(ctx->lens.reserve(v.n * sizeof(uint64_t)));
         v.out_lens = ctx->lens.as<uint64_t>();
@@ -276,7 +341,7 @@ int run_host_batch(aws_huffman_batch_ctx *ctx, const aws_huffman_batch *b, bool 
     }
 
     v.out_lens = b->out_lens ? ctx->lens.as<uint64_t>() : nullptr;
-    if ((encode ? encode_on_device(ctx, v, total_in, st) : decode_on_device(ctx, v, st)) != AWS_OP_SUCCESS)
+    if ((encode ? encode_on_device(ctx, v, total_in, st) : decode_on_device(ctx, v, total_in, st)) != AWS_OP_SUCCESS)
         return AWS_OP_ERR;
 
     if (b->out_lens)
@@ -402,7 +467,22 @@ int aws_huffman_batch_ctx_new(
     HB_CTX_TRY(cudaMalloc(&ctx->d_enc, sizeof(enc)));
     HB_CTX_TRY(cudaMalloc(&ctx->d_lut, (size_t)lut.count * sizeof(uint32_t)));
     HB_CTX_TRY(cudaMemcpy(ctx->d_enc, enc, sizeof(enc), cudaMemcpyHostToDevice));
-    HB_CTX_TRY(cudaMemcpy(ctx->d_lut, lut.entries, (size_t)lut.count * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    {
+        // re-encode for the device: leaf = len << 8 | symbol, link = 0x80000000 | width << 24 | base
+        std::vector<uint32_t> dev(lut.count);
+        for (uint32_t i = 0; i < lut.count; ++i) {
+            const uint32_t e = lut.entries[i];
+            if (e == 0) dev[i] = 0;
+            else if (HUFFMAN_LUT_IS_LEAF(e)) dev[i] = ((uint32_t)HUFFMAN_LUT_LEAF_LEN(e) << 8) | HUFFMAN_LUT_LEAF_SYMBOL(e);
+            else dev[i] = hb::kDevLutLinkFlag | (HUFFMAN_LUT_LINK_WIDTH(e) << 24) | HUFFMAN_LUT_LINK_BASE(e);
+        }
+        HB_CTX_TRY(cudaMemcpy(ctx->d_lut, dev.data(), (size_t)lut.count * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
+    {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device_id) == cudaSuccess && sms > 0)
+            ctx->sm_count = sms;
+    }
 #undef HB_CTX_TRY
 
     ctx->tables.enc = ctx->d_enc;
@@ -430,7 +510,8 @@ void aws_huffman_batch_ctx_destroy(struct aws_huffman_batch_ctx *ctx) {
     }
     if (ctx->d_enc) cudaFree(ctx->d_enc);
     if (ctx->d_lut) cudaFree(ctx->d_lut);
-    GrowBuf *bufs[] = {&ctx->lens,     &ctx->tile_state, &ctx->tile_first, &ctx->s_in,       &ctx->s_in_off,      &ctx->s_out,
+    GrowBuf *bufs[] = {&ctx->lens,     &ctx->tile_state, &ctx->tile_first, &ctx->chunks, &ctx->chunk_lens,
+                       &ctx->chunk_offsets, &ctx->s_in,       &ctx->s_in_off,      &ctx->s_out,
                        &ctx->s_out_off, &ctx->s_caps,     &ctx->s_status,   &ctx->s_consumed,    &ctx->s_ovf_pattern,
                        &ctx->s_ovf_bits, &ctx->s_left_bits, &ctx->s_left_num};
     for (GrowBuf *g : bufs) g->release();
@@ -465,7 +546,7 @@ int aws_huffman_decode_batch_device(
     if (check_batch(batch)) return AWS_OP_ERR;
     HB_CUDA_TRY(cudaSetDevice(ctx->device));
     cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
-    return decode_on_device(ctx, make_view(batch), st);
+    return decode_on_device(ctx, make_view(batch), batch->in_size, st);
 }
 
 int aws_huffman_get_encoded_length_batch(

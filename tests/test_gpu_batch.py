@@ -348,3 +348,62 @@ def test_device_pointer_entry_points(contexts, oracle, oracle_tables):
             st.synchronize()
             assert np.array_equal(back[:len(data)].cpu().numpy(), data)
             assert np.array_equal(back_off.cpu().numpy().view(np.uint64), offs)
+
+
+# ---- long single stream: chunked speculative decode -------------------------------------------------------
+
+@pytest.mark.parametrize("table_name", ["test", "hpack"])
+def test_single_stream_of_arbitrary_bytes(contexts, oracle, oracle_tables, table_name):
+    """Random / corrupted long streams: the true path hits UNKNOWN_SYMBOL somewhere (or ends in padding);
+    symbols, status, cursor and leftover register must match the reference loop exactly."""
+    rng = np.random.default_rng(0x5EED)
+    ctx, table = contexts(table_name), oracle_tables[table_name]
+    sampler = refcodec.zipf_symbol_sampler(refcodec.table_arrays(table_name)[1])
+    clean = np.ascontiguousarray(sampler[rng.integers(0, 65536, size=600_000)])
+    enc = oracle.encode_batch(table, 0xFF, clean, [0, len(clean)], 4 * len(clean) + 64)
+    stream = enc["out"][:int(enc["out_offsets"][-1])].copy()
+    cases = [stream]
+    for where in (len(stream) - 3, len(stream) // 2, 70_000):
+        broken = stream.copy()
+        broken[where:where + 6] = 0xFF  # 48 one-bits: no code in either table
+        cases.append(broken)
+    cases.append(rng.integers(0, 256, size=200_000, dtype=np.uint8))
+    cases.append(np.concatenate([stream[:100_000], np.zeros(50_000, dtype=np.uint8)]))
+    for payload in cases:
+        payload = np.ascontiguousarray(payload)
+        offs = np.array([0, len(payload)], dtype=np.uint64)
+        cap = 2 * len(payload) + 64 if table_name == "hpack" else 2 * len(payload) + 64
+        want = oracle.decode_batch(table, payload, offs, cap)
+        got = ctx.decode(payload, offs, cap)
+        assert_same_packed(got, want)
+
+
+def test_stream_that_never_self_synchronises(pkg, oracle):
+    """A code whose misaligned decodes never find the true boundaries again: symbol 0 has a 4-bit code,
+    every other code is 8 bits with two non-zero nibbles. After one 4-bit code the rest of the stream sits
+    at bit offset 4 mod 8 and every speculative start is wrong, so the repair path must fix it all."""
+    patterns = np.zeros(256, dtype=np.uint32)
+    num_bits = np.zeros(256, dtype=np.uint8)
+    patterns[0], num_bits[0] = 0x0, 4
+    sym = 1
+    for hi in range(1, 16):
+        for lo in range(1, 16):
+            patterns[sym], num_bits[sym] = (hi << 4) | lo, 8
+            sym += 1
+    table = oracle.table(patterns, num_bits)
+    coder = pkg.capi.python_coder(lambda s: (patterns[s], num_bits[s]))
+    ctx = pkg.BatchContext(coder, device=0)
+    rng = np.random.default_rng(4)
+    for n in (70_000, 200_001):
+        data = rng.integers(1, 226, size=n).astype(np.uint8)
+        data[0] = 0
+        data[n // 3] = 0  # shifts alignment back mid-stream
+        offs = np.array([0, n], dtype=np.uint64)
+        want = oracle.encode_batch(table, 0xFF, data, offs, n + 64)
+        got = ctx.encode(data, offs, n + 64)
+        assert_same_packed(got, want)
+        stream = want["out"][:int(want["out_offsets"][-1])]
+        want_d = oracle.decode_batch(table, stream, want["out_offsets"], 2 * n + 64)
+        got_d = ctx.decode(stream, want["out_offsets"], 2 * n + 64)
+        assert_same_packed(got_d, want_d)
+    ctx.close()
