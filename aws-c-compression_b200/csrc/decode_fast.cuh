@@ -216,9 +216,152 @@ __device__ __forceinline__ void leftover_state(
 }
 
 // ---------------------------------------------------------------------------------------------
+// Position-based decode from shared memory.
+//
+// The encoded bytes of a tile are staged in shared memory as BIG-ENDIAN 32-bit words, so the next 32
+// stream bits at bit position `pos` are one funnel shift of two neighbouring words — no bit register
+// to refill, no branches in the common case: window = funnel(word[pos/32], word[pos/32 + 1], pos%32).
+// kPadded: the stream layout of decode_stream_*: every 32-word chunk row is followed by a copy of the
+// next row's first word (row stride 33 words), which keeps lanes that sit at the same offset of
+// different chunks on different banks.
+// ---------------------------------------------------------------------------------------------
+template <bool kPadded>
+__device__ __forceinline__ uint32_t smem_window(const uint32_t *s_in, uint32_t pos) {
+    const uint32_t idx = kPadded ? (pos >> 5) + (pos >> 10) : (pos >> 5);
+    return __funnelshift_l(s_in[idx + 1], s_in[idx], pos);
+}
+
+// Packs symbols into aligned 32-bit global stores; one PRMT per symbol, byte stores only for the
+// first and last partial word of the span.
+struct WordWriter {
+    uint8_t *base;   // out + off rounded down to 4 bytes
+    uint32_t phase;  // off & 3
+    uint32_t k;      // phase + symbols so far
+    uint32_t pack;
+    uint64_t room;   // bytes that may be written from `out + off`
+
+    __device__ __forceinline__ void init(uint8_t *out, uint64_t out_room) {
+        phase = (uint32_t)(reinterpret_cast<uintptr_t>(out) & 3);
+        base = out - phase;
+        k = phase;
+        pack = 0;
+        room = out_room;
+    }
+    __device__ __forceinline__ void put(uint32_t entry) {
+        pack = __byte_perm(pack, entry, 0x4321);  // shift in the symbol (low byte of the LUT entry)
+        ++k;
+        if ((k & 3u) == 0) {
+            const uint32_t done = k - phase;  // symbols so far
+            if (k == 4 && phase != 0) {
+                // first word is shared with the previous span: only our bytes
+                for (uint32_t i = phase; i < 4; ++i)
+                    if (i - phase < room) base[i] = (uint8_t)(pack >> (8 * i));
+            } else if (done <= room) {
+                *reinterpret_cast<uint32_t *>(base + k - 4) = pack;
+            } else {
+                for (uint32_t i = 0; i < 4; ++i)
+                    if (done - 4 + i < room) base[k - 4 + i] = (uint8_t)(pack >> (8 * i));
+            }
+        }
+    }
+    __device__ __forceinline__ void finish() {
+        const uint32_t tail = k & 3u;  // symbols waiting in `pack` (its top `tail` bytes)
+        if (tail == 0) return;
+        const uint32_t first = (k < 4) ? phase : 0u;  // the span never completed a word
+        const uint32_t word0 = k - tail;              // byte offset of the open word from `base`
+        for (uint32_t i = first; i < tail; ++i) {
+            const uint64_t sym_index = (uint64_t)(word0 + i) - phase;
+            if (sym_index < room) base[word0 + i] = (uint8_t)(pack >> (8 * (4 - tail + i)));
+        }
+    }
+};
+
+struct SpanS {
+    uint32_t pos;   // stage-relative bit position after the last decoded symbol
+    uint32_t nsym;
+    uint32_t term;
+};
+
+// Decodes from stage bit `pos` until `stop`; the stream itself ends at `end` (stop <= end; both are
+// stage-relative bit positions). Same rules as decode_span.
+template <bool kWrite, bool kPadded, bool kSkipHoles>
+__device__ __forceinline__ SpanS decode_smem(
+    const uint32_t *s_in, const uint32_t *s_lut, uint32_t root_bits, uint32_t pos, uint32_t stop, uint32_t end,
+    WordWriter *writer) {
+    SpanS r;
+    uint32_t nsym = 0;
+    uint32_t term = kTermStop;
+    // fast region: at least 32 real bits follow `pos`, so a match can never lean on the zero fill and a
+    // hole is an error straight away
+    const uint32_t fast_end = (end >= 32u) ? min(stop, end - 31u) : 0u;
+    while (pos < fast_end) {
+        uint32_t e = s_lut[smem_window<kPadded>(s_in, pos) >> (32 - root_bits)];
+        if (e - 0x100u >= 0x7fffff00u) {  // not a plain leaf: link or hole
+            if ((int32_t)e < 0) {
+                const uint32_t window = smem_window<kPadded>(s_in, pos);
+                uint32_t used = root_bits;
+                do {
+                    const uint32_t width = (e >> 24) & 0x7fu;
+                    e = s_lut[(e & 0xFFFFFFu) + ((window << used) >> (32 - width))];
+                    used += width;
+                } while ((int32_t)e < 0);
+            }
+            if (e == 0) {
+                if (kSkipHoles) {
+                    ++pos;
+                    continue;
+                }
+                term = kTermUnknown;
+                break;
+            }
+        }
+        pos += e >> 8;
+        ++nsym;
+        if (kWrite) writer->put(e);
+    }
+    if (term == kTermStop && pos < stop) {
+        // fewer than 32 bits of stream remain: the window is the stream zero-extended
+        while (true) {
+            const uint32_t left = end - pos;
+            if (left == 0) { term = kTermEnd; break; }
+            const uint32_t window = smem_window<kPadded>(s_in, pos) & (0xffffffffu << (32 - left));
+            const uint32_t e = dec_lookup(s_lut, root_bits, window);
+            if (e == 0) {
+                if (kSkipHoles && left > 1) {
+                    ++pos;
+                    if (pos >= stop) break;
+                    continue;
+                }
+                term = kTermEnd;  // fewer than 32 bits left: treated as padding (huffman.c:240-244)
+                break;
+            }
+            const uint32_t used = e >> 8;
+            if (used > left) { term = kTermEnd; break; }
+            pos += used;
+            ++nsym;
+            if (kWrite) writer->put(e);
+            if (pos >= stop) {
+                if (pos >= end) term = kTermEnd;
+                break;
+            }
+        }
+    } else if (term == kTermStop && pos >= end) {
+        term = kTermEnd;
+    }
+    r.pos = pos;
+    r.nsym = nsym;
+    r.term = term;
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Batch of independent strings
 // ---------------------------------------------------------------------------------------------
 constexpr int kDecThreads = 128;
+constexpr int kDecWarps = kDecThreads / 32;
+constexpr int kDecItemsPerTile = 256;          // strings per tile
+constexpr int kDecGroups = kDecItemsPerTile / 32;
+constexpr uint32_t kDecStageWords = 8 * 1024;  // 32 KiB of encoded bytes per tile
 
 struct DecBatchArgs {
     BatchView b;
@@ -230,79 +373,200 @@ struct DecBatchArgs {
     uint32_t num_tiles;
 };
 
+// One thread per string, but strings are first SORTED BY LENGTH inside the tile (counting sort in
+// shared memory) and handed to warps in groups of 32 similar lengths, longest first: a warp's lanes
+// then leave the decode loop almost together instead of waiting for the longest string of a random
+// group, and warps pull groups dynamically so the block stays busy.
+// Dynamic shared memory: [LUT][stage words + 2 zero words]
 __global__ void __launch_bounds__(kDecThreads) decode_batch_kernel(DecBatchArgs a) {
-    extern __shared__ uint32_t s_lut[];
-    __shared__ uint64_t s_warp_sum[kDecThreads / 32];
+    extern __shared__ uint32_t s_lut[];  // [LUT][stage]
+    uint32_t *s_in = s_lut + a.lut_count;
+    __shared__ uint32_t s_start[kDecItemsPerTile];  // first bit of the string in the stage
+    __shared__ uint32_t s_bytes[kDecItemsPerTile];  // encoded length
+    __shared__ uint32_t s_cnt[kDecItemsPerTile];    // symbols per string, then exclusive offsets within the tile
+    __shared__ uint16_t s_perm[kDecItemsPerTile];   // strings in order of decreasing length
+    __shared__ uint32_t s_hist[256];
+    __shared__ uint64_t s_warp_sum[kDecWarps];
     __shared__ uint64_t s_prefix;
-    __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_tile, s_next;
 
     for (uint32_t i = threadIdx.x; i < a.lut_count; i += kDecThreads) s_lut[i] = a.lut[i];
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
     const BatchView &b = a.b;
 
     while (true) {
-        __syncthreads();  // s_tile / s_prefix / s_warp_sum reuse, and the LUT on the first trip
-        if (threadIdx.x == 0) s_tile = atomicAdd(a.ticket, 1u);
+        __syncthreads();  // previous tile fully done (and the LUT is in place on the first trip)
+        if (threadIdx.x == 0) {
+            s_tile = atomicAdd(a.ticket, 1u);
+            s_next = kDecWarps;
+        }
+        for (uint32_t i = threadIdx.x; i < 256; i += kDecThreads) s_hist[i] = 0;
         __syncthreads();
         const uint32_t tile = s_tile;
         if (tile >= a.num_tiles) break;
-        const uint64_t item = (uint64_t)tile * kDecThreads + threadIdx.x;
-        const bool live = item < b.n;
+        const uint64_t item0 = (uint64_t)tile * kDecItemsPerTile;
+        const uint32_t nitems = (uint32_t)min((uint64_t)kDecItemsPerTile, b.n - item0);
+        const uint32_t ngroups = (nitems + 31) / 32;
 
-        uint64_t in0 = 0, len = 0;
-        if (live) {
-            in0 = b.in_offsets[item];
-            len = b.in_offsets[item + 1] - in0;
+        // ---- stage the tile's encoded bytes as big-endian words; histogram of string lengths -----------------
+        const uint64_t byte0 = b.in_offsets[item0], byte1 = b.in_offsets[item0 + nitems];
+        const uintptr_t addr0 = reinterpret_cast<uintptr_t>(b.in) + byte0;
+        const uint32_t lead = (uint32_t)(addr0 & 3);
+        const uint64_t nwords64 = (byte1 - byte0 + lead + 3) >> 2;
+        const bool staged = nwords64 <= kDecStageWords;
+        if (staged) {
+            const uint32_t nwords = (uint32_t)nwords64;
+            const uint32_t *gw = reinterpret_cast<const uint32_t *>(addr0 - lead);
+            for (uint32_t j = threadIdx.x; j < nwords; j += kDecThreads) s_in[j] = __byte_perm(__ldg(gw + j), 0, 0x0123);
+            if (threadIdx.x < 2) s_in[nwords + threadIdx.x] = 0;
         }
-        const uint8_t *src = b.in + in0;
+        for (uint32_t it = threadIdx.x; it < nitems; it += kDecThreads) {
+            const uint64_t in0 = b.in_offsets[item0 + it];
+            const uint64_t len = b.in_offsets[item0 + it + 1] - in0;
+            s_start[it] = (uint32_t)(in0 - byte0) * 8 + lead * 8;
+            s_bytes[it] = (uint32_t)min(len, (uint64_t)0xffffffffu);
+            atomicAdd(&s_hist[255 - (uint32_t)min(len, (uint64_t)255)], 1u);
+        }
+        __syncthreads();
+        if (warp == 0) {
+            // exclusive scan of the 256 bins, 8 per lane
+            uint32_t v[8], sum = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                v[i] = s_hist[lane * 8 + i];
+                sum += v[i];
+            }
+            uint32_t run = warp_inclusive_scan(sum) - sum;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                s_hist[lane * 8 + i] = run;
+                run += v[i];
+            }
+        }
+        __syncthreads();
+        for (uint32_t it = threadIdx.x; it < nitems; it += kDecThreads) {
+            const uint32_t rank = atomicAdd(&s_hist[255 - min(s_bytes[it], 255u)], 1u);
+            s_perm[rank] = (uint16_t)it;
+        }
+        __syncthreads();
 
-        // ---- count ---------------------------------------------------------------------------------------
-        DecodeSpan c = {0, 0, kTermEnd};
-        if (live) c = decode_span<false, false>(s_lut, a.root_bits, src, 0, len * 8, len, nullptr);
+        // ---- count ---------------------------------------------------------------------------------------------
+        for (uint32_t g = warp; g < ngroups;) {
+            const uint32_t slot = g * 32 + lane;
+            if (slot < nitems) {
+                const uint32_t it = s_perm[slot];
+                const uint64_t item = item0 + it;
+                const uint32_t nbytes = s_bytes[it];
+                uint64_t cbits;
+                uint32_t nsym, term;
+                if (staged) {
+                    const uint32_t ib = s_start[it], ie = ib + nbytes * 8;
+                    const SpanS r = decode_smem<false, false, false>(s_in, s_lut, a.root_bits, ib, ie, ie, nullptr);
+                    cbits = r.pos - ib;
+                    nsym = r.nsym;
+                    term = r.term;
+                } else {
+                    const uint64_t in0 = b.in_offsets[item];
+                    const uint64_t len = b.in_offsets[item + 1] - in0;
+                    const DecodeSpan r = decode_span<false, false>(s_lut, a.root_bits, b.in + in0, 0, len * 8, len, nullptr);
+                    cbits = r.pos;
+                    nsym = (uint32_t)r.nsym;
+                    term = r.term;
+                }
+                s_cnt[it] = nsym;
+                if (b.status) b.status[item] = term == kTermUnknown ? kStatusUnknownSymbol : kStatusOk;
+                if (b.consumed || b.leftover_working_bits || b.leftover_num_bits) {
+                    const uint64_t in0 = b.in_offsets[item];
+                    leftover_state(
+                        b.in + in0, b.in_offsets[item + 1] - in0, cbits, term == kTermUnknown,
+                        b.consumed ? b.consumed + item : nullptr,
+                        b.leftover_working_bits ? b.leftover_working_bits + item : nullptr,
+                        b.leftover_num_bits ? b.leftover_num_bits + item : nullptr);
+                }
+            }
+            uint32_t next = 0;
+            if (lane == 0) next = atomicAdd(&s_next, 1u);
+            g = __shfl_sync(0xffffffffu, next, 0);
+        }
+        __syncthreads();
 
-        // ---- offsets: block scan + look-back ----------------------------------------------------------------
-        const uint64_t incl = warp_inclusive_scan64(c.nsym);
+        // ---- offsets: block scan (2 strings per thread) + look-back --------------------------------------------
+        const uint32_t c0 = 2 * threadIdx.x < nitems ? s_cnt[2 * threadIdx.x] : 0u;
+        const uint32_t c1 = 2 * threadIdx.x + 1 < nitems ? s_cnt[2 * threadIdx.x + 1] : 0u;
+        const uint64_t mine = (uint64_t)c0 + c1;
+        const uint64_t incl = warp_inclusive_scan64(mine);
         if (lane == 31) s_warp_sum[warp] = incl;
         __syncthreads();
         if (warp == 0) {
-            uint64_t w = lane < kDecThreads / 32 ? s_warp_sum[lane] : 0;
+            uint64_t w = lane < kDecWarps ? s_warp_sum[lane] : 0;
             const uint64_t wi = warp_inclusive_scan64(w);
-            if (lane < kDecThreads / 32) s_warp_sum[lane] = wi - w;
-            const uint64_t total = __shfl_sync(0xffffffffu, wi, kDecThreads / 32 - 1);
+            if (lane < kDecWarps) s_warp_sum[lane] = wi - w;
+            const uint64_t total = __shfl_sync(0xffffffffu, wi, kDecWarps - 1);
             const uint64_t prefix = lookback_exclusive_prefix(a.tile_state, tile, total);
             if (lane == 0) s_prefix = prefix;
         }
         __syncthreads();
-        const uint64_t off = s_prefix + s_warp_sum[warp] + (incl - c.nsym);
-
-        if (live) {
-            b.out_offsets[item] = off;
-            if (item + 1 == b.n) b.out_offsets[b.n] = off + c.nsym;
-            if (b.out_lens) b.out_lens[item] = c.nsym;
-            if (b.status) b.status[item] = c.term == kTermUnknown ? kStatusUnknownSymbol : kStatusOk;
-            if (b.consumed || b.leftover_working_bits || b.leftover_num_bits)
-                leftover_state(
-                    src, len, c.pos, c.term == kTermUnknown, b.consumed ? b.consumed + item : nullptr,
-                    b.leftover_working_bits ? b.leftover_working_bits + item : nullptr,
-                    b.leftover_num_bits ? b.leftover_num_bits + item : nullptr);
-
-            // ---- write -----------------------------------------------------------------------------------------
-            if (c.nsym) {
-                ByteWriter wr;
-                wr.init(b.out + off, off < b.out_capacity ? b.out_capacity - off : 0);
-                decode_span<true, false>(s_lut, a.root_bits, src, 0, len * 8, len, &wr);
-                wr.finish();
+        {
+            const uint64_t tile_base = s_prefix;
+            const uint64_t e0 = s_warp_sum[warp] + (incl - mine);  // exclusive, within the tile
+            if (2 * threadIdx.x < nitems) {
+                s_cnt[2 * threadIdx.x] = (uint32_t)e0;
+                b.out_offsets[item0 + 2 * threadIdx.x] = tile_base + e0;
+                if (b.out_lens) b.out_lens[item0 + 2 * threadIdx.x] = c0;
+                if (item0 + 2 * threadIdx.x + 1 == b.n) b.out_offsets[b.n] = tile_base + e0 + c0;
             }
+            if (2 * threadIdx.x + 1 < nitems) {
+                s_cnt[2 * threadIdx.x + 1] = (uint32_t)(e0 + c0);
+                b.out_offsets[item0 + 2 * threadIdx.x + 1] = tile_base + e0 + c0;
+                if (b.out_lens) b.out_lens[item0 + 2 * threadIdx.x + 1] = c1;
+                if (item0 + 2 * threadIdx.x + 2 == b.n) b.out_offsets[b.n] = tile_base + e0 + c0 + c1;
+            }
+            if (threadIdx.x == 0) s_next = kDecWarps;
+        }
+        __syncthreads();
+
+        // ---- write: decode again, now storing -------------------------------------------------------------------
+        const uint64_t tile_base = s_prefix;
+        for (uint32_t g = warp; g < ngroups;) {
+            const uint32_t slot = g * 32 + lane;
+            if (slot < nitems) {
+                const uint32_t it = s_perm[slot];
+                const uint64_t off = tile_base + s_cnt[it];
+                const uint64_t room = off < b.out_capacity ? b.out_capacity - off : 0;
+                if (staged) {
+                    WordWriter wr;
+                    wr.init(b.out + off, room);
+                    const uint32_t ib = s_start[it], ie = ib + s_bytes[it] * 8;
+                    decode_smem<true, false, false>(s_in, s_lut, a.root_bits, ib, ie, ie, &wr);
+                    wr.finish();
+                } else {
+                    const uint64_t in0 = b.in_offsets[item0 + it];
+                    const uint64_t len = b.in_offsets[item0 + it + 1] - in0;
+                    ByteWriter wr;
+                    wr.init(b.out + off, room);
+                    decode_span<true, false>(s_lut, a.root_bits, b.in + in0, 0, len * 8, len, &wr);
+                    wr.finish();
+                }
+            }
+            uint32_t next = 0;
+            if (lane == 0) next = atomicAdd(&s_next, 1u);
+            g = __shfl_sync(0xffffffffu, next, 0);
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 // One long stream
+//
+// Positions are bits in "aligned space": bit 0 is the first bit of the 4-byte aligned word that holds
+// the stream's first byte, so chunk k is exactly the aligned words [32k, 32k + 32) and the stream
+// occupies [begin_bit, end_bit) = [8 * lead, 8 * (lead + len)).
 // ---------------------------------------------------------------------------------------------
 constexpr uint32_t kChunkBits = 1024;   // 128 encoded bytes per thread
 constexpr uint32_t kPrerollBits = 256;  // HPACK on Zipf data: 99.4 % of starts are in sync by then
 constexpr int kStreamThreads = 128;
+constexpr uint32_t kStreamRowWords = 33;                                      // 32 words + 1 copy of the next row's first
+constexpr uint32_t kStreamStageWords = (kStreamThreads + 1) * kStreamRowWords + 1;  // previous chunk + 128 own
 
 // Per-chunk record, one 64-bit word so it is always read and written whole:
 //   [15:0]  entry offset  (first code boundary at or after the chunk start, relative to it)
@@ -319,41 +583,80 @@ __device__ __forceinline__ uint32_t chunk_nsym(uint64_t w) { return (uint32_t)((
 __device__ __forceinline__ uint32_t chunk_term(uint64_t w) { return (uint32_t)((w >> 48) & 3u); }
 
 struct StreamArgs {
-    const uint8_t *in;       // the item's first byte
-    uint64_t len;            // encoded bytes
+    const uint8_t *in_aligned;  // the stream's first byte, rounded down to 4 bytes
+    uint64_t begin_bit;         // 8 * lead
+    uint64_t end_bit;           // 8 * (lead + len)
     uint64_t num_chunks;
-    uint64_t *chunks;        // num_chunks records
-    uint64_t *chunk_offsets; // num_chunks + 1 output offsets (after the scan)
-    uint64_t *control;       // [0] = first inconsistent chunk (or ~0), [1] = first terminated chunk (or ~0)
+    uint64_t *chunks;           // num_chunks records
+    uint64_t *chunk_offsets;    // num_chunks + 1 output offsets (after the scan)
+    uint64_t *control;          // [0] = first inconsistent chunk (or ~0), [1] = first terminated chunk (or ~0)
     const uint32_t *lut;
     uint32_t lut_count;
     uint32_t root_bits;
 };
 
+// (re)decodes one chunk from global memory; used by the rare fix-up paths
 __device__ __forceinline__ uint64_t decode_chunk_record(
     const uint32_t *s_lut, const StreamArgs &a, uint64_t k, uint32_t entry) {
     const uint64_t begin = k * kChunkBits;
-    const uint64_t stop = min(begin + kChunkBits, a.len * 8);
-    const DecodeSpan r = decode_span<false, false>(s_lut, a.root_bits, a.in, begin + entry, stop, a.len, nullptr);
+    const uint64_t stop = min(begin + kChunkBits, a.end_bit);
+    const DecodeSpan r =
+        decode_span<false, false>(s_lut, a.root_bits, a.in_aligned, begin + entry, stop, a.end_bit >> 3, nullptr);
     const uint32_t exit = r.term == kTermStop ? (uint32_t)(r.pos - stop) : 0u;
     return chunk_pack(entry, exit, (uint32_t)r.nsym, r.term);
 }
 
+// Stages chunks [c0 - 1, c0 + 128] of the stream as big-endian words in the padded row layout and
+// zeroes everything outside [begin, end). Stage bit 0 is the first bit of chunk c0 - 1.
+__device__ __forceinline__ void stream_stage(const StreamArgs &a, uint64_t c0, uint32_t *s_in) {
+    const uint32_t *gw = reinterpret_cast<const uint32_t *>(a.in_aligned);
+    const uint64_t end_byte = a.end_bit >> 3;
+    const uint64_t nwords_valid = (end_byte + 3) >> 2;
+    // rows 0..128 hold 32 words each; word 32 of a row duplicates word 0 of the next row
+    for (uint32_t i = threadIdx.x; i < (kStreamThreads + 1) * 32 + 1; i += kStreamThreads) {
+        const uint32_t row = i >> 5, col = i & 31;
+        const int64_t w = ((int64_t)c0 - 1 + row) * 32 + col;  // aligned word index in the stream
+        uint32_t v = 0;
+        if (w >= 0 && (uint64_t)w < nwords_valid) {
+            v = __byte_perm(__ldg(gw + w), 0, 0x0123);
+            const uint64_t first_byte = (uint64_t)w * 4;
+            if (first_byte + 4 > end_byte) v &= 0xffffffffu << (8 * (first_byte + 4 - end_byte));
+        }
+        if (row <= kStreamThreads) s_in[row * kStreamRowWords + col] = v;
+        if (col == 0 && row > 0) s_in[(row - 1) * kStreamRowWords + 32] = v;
+    }
+}
+
 // Speculative pass: find an entry point by pre-rolling, then decode the chunk once.
 __global__ void __launch_bounds__(kStreamThreads) stream_sync_kernel(StreamArgs a) {
-    extern __shared__ uint32_t s_lut[];
+    extern __shared__ uint32_t s_lut[];  // [LUT][stage]
+    uint32_t *s_in = s_lut + a.lut_count;
     for (uint32_t i = threadIdx.x; i < a.lut_count; i += kStreamThreads) s_lut[i] = a.lut[i];
-    __syncthreads();
-    for (uint64_t k = (uint64_t)blockIdx.x * kStreamThreads + threadIdx.x; k < a.num_chunks;
-         k += (uint64_t)gridDim.x * kStreamThreads) {
+    const uint64_t num_tiles = (a.num_chunks + kStreamThreads - 1) / kStreamThreads;
+    for (uint64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const uint64_t c0 = t * kStreamThreads;
+        __syncthreads();
+        stream_stage(a, c0, s_in);
+        __syncthreads();
+        const uint64_t k = c0 + threadIdx.x;
+        if (k >= a.num_chunks) continue;
+        const uint64_t origin = (c0 - 1) * kChunkBits;  // wraps for c0 == 0; differences below stay exact
         const uint64_t begin = k * kChunkBits;
-        uint32_t entry = 0;
-        if (k != 0) {
-            const uint64_t from = begin > kPrerollBits ? begin - kPrerollBits : 0;
-            const DecodeSpan pre = decode_span<false, true>(s_lut, a.root_bits, a.in, from, begin, a.len, nullptr);
-            entry = pre.pos >= begin ? (uint32_t)(pre.pos - begin) : 0u;
+        const uint64_t stop = min(begin + kChunkBits, a.end_bit);
+        const uint32_t s_begin = (uint32_t)(begin - origin), s_stop = (uint32_t)(stop - origin);
+        const uint32_t s_end = (uint32_t)min(a.end_bit - origin, (uint64_t)(kStreamThreads + 2) * kChunkBits);
+        uint32_t entry;
+        if (begin <= a.begin_bit) {
+            entry = (uint32_t)(a.begin_bit - begin);  // the stream starts inside this chunk: exact
+        } else {
+            const uint64_t from = max(begin - kPrerollBits, a.begin_bit);
+            const SpanS pre =
+                decode_smem<false, true, true>(s_in, s_lut, a.root_bits, (uint32_t)(from - origin), s_begin, s_end, nullptr);
+            entry = pre.pos >= s_begin ? pre.pos - s_begin : 0u;
         }
-        a.chunks[k] = decode_chunk_record(s_lut, a, k, entry);
+        const SpanS r = decode_smem<false, true, false>(s_in, s_lut, a.root_bits, s_begin + entry, s_stop, s_end, nullptr);
+        const uint32_t exit = r.term == kTermStop ? r.pos - s_stop : 0u;
+        a.chunks[k] = chunk_pack(entry, exit, r.nsym, r.term);
     }
 }
 
@@ -368,6 +671,7 @@ __global__ void __launch_bounds__(kStreamThreads) stream_fix_kernel(StreamArgs a
         const uint64_t prev = ld_relaxed_u64(&a.chunks[k - 1]);
         const uint64_t mine = ld_relaxed_u64(&a.chunks[k]);
         if (chunk_term(prev) != kTermStop) continue;  // the stream ended before this chunk
+        if (k * kChunkBits <= a.begin_bit) continue;  // the chunk the stream starts in has an exact entry
         if (chunk_entry(mine) != chunk_exit(prev))
             st_relaxed_u64(&a.chunks[k], decode_chunk_record(s_lut, a, k, chunk_exit(prev)));
     }
@@ -382,7 +686,9 @@ __global__ void __launch_bounds__(256) stream_verify_kernel(StreamArgs a) {
         if (chunk_term(mine) != kTermStop && k < term) term = k;
         if (k > 0) {
             const uint64_t prev = a.chunks[k - 1];
-            if (chunk_term(prev) == kTermStop && chunk_entry(mine) != chunk_exit(prev) && k < bad) bad = k;
+            if (chunk_term(prev) == kTermStop && k * kChunkBits > a.begin_bit &&
+                chunk_entry(mine) != chunk_exit(prev) && k < bad)
+                bad = k;
         }
     }
 #pragma unroll
@@ -433,32 +739,41 @@ __global__ void __launch_bounds__(256) stream_counts_kernel(StreamArgs a, uint64
 
 // Final pass: every chunk up to the terminating one decodes again, now writing.
 __global__ void __launch_bounds__(kStreamThreads) stream_write_kernel(StreamArgs a, BatchView b) {
-    extern __shared__ uint32_t s_lut[];
+    extern __shared__ uint32_t s_lut[];  // [LUT][stage]
+    uint32_t *s_in = s_lut + a.lut_count;
     for (uint32_t i = threadIdx.x; i < a.lut_count; i += kStreamThreads) s_lut[i] = a.lut[i];
-    __syncthreads();
     const uint64_t first_term = a.control[1];
     const uint64_t last = first_term < a.num_chunks ? first_term : a.num_chunks - 1;
-    for (uint64_t k = (uint64_t)blockIdx.x * kStreamThreads + threadIdx.x; k <= last;
-         k += (uint64_t)gridDim.x * kStreamThreads) {
+    const uint64_t num_tiles = last / kStreamThreads + 1;
+    for (uint64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const uint64_t c0 = t * kStreamThreads;
+        __syncthreads();
+        stream_stage(a, c0, s_in);
+        __syncthreads();
+        const uint64_t k = c0 + threadIdx.x;
+        if (k > last) continue;
+        const uint64_t origin = (c0 - 1) * kChunkBits;
         const uint64_t rec = a.chunks[k];
         const uint64_t begin = k * kChunkBits;
-        const uint64_t stop = min(begin + kChunkBits, a.len * 8);
+        const uint64_t stop = min(begin + kChunkBits, a.end_bit);
+        const uint32_t s_end = (uint32_t)min(a.end_bit - origin, (uint64_t)(kStreamThreads + 2) * kChunkBits);
         const uint64_t off = a.chunk_offsets[k];
-        ByteWriter wr;
+        WordWriter wr;
         wr.init(b.out + off, off < b.out_capacity ? b.out_capacity - off : 0);
-        const DecodeSpan r =
-            decode_span<true, false>(s_lut, a.root_bits, a.in, begin + chunk_entry(rec), stop, a.len, &wr);
+        const SpanS r = decode_smem<true, true, false>(
+            s_in, s_lut, a.root_bits, (uint32_t)(begin - origin) + chunk_entry(rec), (uint32_t)(stop - origin), s_end, &wr);
         wr.finish();
         if (k == last) {
             // item-level results (n == 1)
             const uint64_t total = off + r.nsym;
+            const uint64_t cbits = (uint64_t)r.pos + origin - a.begin_bit;  // stream bits turned into symbols
             b.out_offsets[0] = 0;
             b.out_offsets[1] = total;
             if (b.out_lens) b.out_lens[0] = total;
             if (b.status) b.status[0] = r.term == kTermUnknown ? kStatusUnknownSymbol : kStatusOk;
             if (b.consumed || b.leftover_working_bits || b.leftover_num_bits)
-                leftover_state(a.in, a.len, r.pos, r.term == kTermUnknown, b.consumed, b.leftover_working_bits,
-                               b.leftover_num_bits);
+                leftover_state(a.in_aligned + (a.begin_bit >> 3), (a.end_bit - a.begin_bit) >> 3, cbits,
+                               r.term == kTermUnknown, b.consumed, b.leftover_working_bits, b.leftover_num_bits);
         }
     }
 }

@@ -201,7 +201,7 @@ int encode_on_device(aws_huffman_batch_ctx *ctx, hb::BatchView v, uint64_t total
 
 // Packed layout, many strings: fused count -> look-back -> write kernel (one thread per string).
 int decode_batch_fast(aws_huffman_batch_ctx *ctx, const hb::BatchView &v, cudaStream_t stream) {
-    const uint64_t num_tiles = (v.n + kDecThreads - 1) / kDecThreads;
+    const uint64_t num_tiles = (v.n + kDecItemsPerTile - 1) / kDecItemsPerTile;
     const size_t state_bytes = num_tiles * sizeof(uint64_t) + 256;
     HB_CUDA_TRY(ctx->tile_state.reserve(state_bytes));
     HB_CUDA_TRY(cudaMemsetAsync(ctx->tile_state.ptr, 0, state_bytes, stream));
@@ -213,8 +213,10 @@ int decode_batch_fast(aws_huffman_batch_ctx *ctx, const hb::BatchView &v, cudaSt
     a.tile_state = ctx->tile_state.as<uint64_t>();
     a.ticket = reinterpret_cast<uint32_t *>(a.tile_state + num_tiles);
     a.num_tiles = (uint32_t)num_tiles;
-    const unsigned blocks = (unsigned)std::min<uint64_t>(num_tiles, (uint64_t)ctx->sm_count * 12);
-    decode_batch_kernel<<<blocks, kDecThreads, ctx->tables.lut_count * sizeof(uint32_t), stream>>>(a);
+    const size_t smem = ((size_t)ctx->tables.lut_count + kDecStageWords + 2) * sizeof(uint32_t);
+    HB_CUDA_TRY(cudaFuncSetAttribute(decode_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned blocks = (unsigned)std::min<uint64_t>(num_tiles, (uint64_t)ctx->sm_count * 4);
+    decode_batch_kernel<<<blocks, kDecThreads, smem, stream>>>(a);
     ++ctx->launches;
     HB_CUDA_TRY(cudaGetLastError());
     return AWS_OP_SUCCESS;
@@ -222,13 +224,16 @@ int decode_batch_fast(aws_huffman_batch_ctx *ctx, const hb::BatchView &v, cudaSt
 
 // Packed layout, one long stream: chunked speculative decode.
 int decode_stream_fast(aws_huffman_batch_ctx *ctx, const hb::BatchView &v, uint64_t len, cudaStream_t stream) {
-    const uint64_t num_chunks = (len * 8 + kChunkBits - 1) / kChunkBits;
+    const uint64_t lead = reinterpret_cast<uintptr_t>(v.in) & 3;
+    const uint64_t end_bit = (lead + len) * 8;
+    const uint64_t num_chunks = (end_bit + kChunkBits - 1) / kChunkBits;
     HB_CUDA_TRY(ctx->chunks.reserve(num_chunks * sizeof(uint64_t) + 64));
     HB_CUDA_TRY(ctx->chunk_lens.reserve(num_chunks * sizeof(uint64_t)));
     HB_CUDA_TRY(ctx->chunk_offsets.reserve((num_chunks + 1) * sizeof(uint64_t)));
     StreamArgs a{};
-    a.in = v.in;
-    a.len = len;
+    a.in_aligned = v.in - lead;
+    a.begin_bit = lead * 8;
+    a.end_bit = end_bit;
     a.num_chunks = num_chunks;
     a.chunks = ctx->chunks.as<uint64_t>();
     a.chunk_offsets = ctx->chunk_offsets.as<uint64_t>();
@@ -238,10 +243,13 @@ int decode_stream_fast(aws_huffman_batch_ctx *ctx, const hb::BatchView &v, uint6
     a.root_bits = ctx->tables.lut_root_bits;
     HB_CUDA_TRY(cudaMemsetAsync(a.control, 0xff, 2 * sizeof(uint64_t), stream));
     const size_t smem = ctx->tables.lut_count * sizeof(uint32_t);
+    const size_t smem_staged = smem + kStreamStageWords * sizeof(uint32_t);
+    HB_CUDA_TRY(cudaFuncSetAttribute(stream_sync_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_staged));
+    HB_CUDA_TRY(cudaFuncSetAttribute(stream_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_staged));
     const unsigned wide = (unsigned)std::min<uint64_t>((num_chunks + kStreamThreads - 1) / kStreamThreads,
                                                        (uint64_t)ctx->sm_count * 12);
     const unsigned flat = (unsigned)std::min<uint64_t>((num_chunks + 255) / 256, (uint64_t)ctx->sm_count * 8);
-    stream_sync_kernel<<<wide, kStreamThreads, smem, stream>>>(a);
+    stream_sync_kernel<<<wide, kStreamThreads, smem_staged, stream>>>(a);
     for (int round = 0; round < 2; ++round) stream_fix_kernel<<<wide, kStreamThreads, smem, stream>>>(a);
     stream_verify_kernel<<<flat, 256, 0, stream>>>(a);
     stream_repair_kernel<<<1, 32, smem, stream>>>(a);
@@ -249,7 +257,7 @@ int decode_stream_fast(aws_huffman_batch_ctx *ctx, const hb::BatchView &v, uint6
     ctx->launches += 6;
     HB_CUDA_TRY(cudaGetLastError());
     if (launch_scan(ctx, ctx->chunk_lens.as<uint64_t>(), a.chunk_offsets, num_chunks, stream)) return AWS_OP_ERR;
-    stream_write_kernel<<<wide, kStreamThreads, smem, stream>>>(a, v);
+    stream_write_kernel<<<wide, kStreamThreads, smem_staged, stream>>>(a, v);
     ++ctx->launches;
     HB_CUDA_TRY(cudaGetLastError());
     return AWS_OP_SUCCESS;
