@@ -28,19 +28,20 @@ namespace hb {
 
 constexpr uint32_t kDecLutMaxSmem = 8192;  // entries (32 KiB); larger tables use the generic kernels
 
-// Device LUT entry (converted from host/huffman_lut.h at context creation):
-//   leaf: len << 8 | symbol   (len 1..32)      link: 0x80000000 | width << 24 | base      hole: 0
-__device__ __forceinline__ uint32_t dec_lookup(const uint32_t *s_lut, uint32_t root_bits, uint32_t window) {
-    uint32_t e = s_lut[window >> (32 - root_bits)];
-    if ((int32_t)e < 0) {
-        uint32_t used = root_bits;
-        do {
-            const uint32_t width = (e >> 24) & 0x7fu;
-            e = s_lut[(e & 0xFFFFFFu) + ((window << used) >> (32 - width))];
-            used += width;
-        } while ((int32_t)e < 0);
+// Full lookup of one window (device LUT format: device_common.cuh). Returns a leaf entry or 0 (hole);
+// callers that want one symbol at a time use dlut_len1 / dlut_sym1 of the result.
+__device__ __forceinline__ uint32_t dec_walk(const uint32_t *s_lut, uint32_t root_bits, uint32_t window, uint32_t e) {
+    uint32_t used = root_bits;
+    while (e != 0 && !dlut_is_leaf(e)) {
+        const uint32_t width = dlut_link_width(e);
+        e = s_lut[dlut_link_base(e) + ((window << used) >> (32 - width))];
+        used += width;
     }
     return e;
+}
+__device__ __forceinline__ uint32_t dec_lookup(const uint32_t *s_lut, uint32_t root_bits, uint32_t window) {
+    const uint32_t e = s_lut[window >> (32 - root_bits)];
+    return dlut_is_leaf(e) ? e : dec_walk(s_lut, root_bits, window, e);
 }
 
 enum : uint32_t {
@@ -180,12 +181,12 @@ __device__ __forceinline__ DecodeSpan decode_span(
             r.term = bits_left < 32 ? kTermEnd : kTermUnknown;
             break;
         }
-        const uint32_t used = e >> 8;
+        const uint32_t used = dlut_len1(e);
         if (used > bits_left) { r.term = kTermEnd; break; }
         br.consume(used);
         pos += used;
         ++nsym;
-        if (kWrite) writer->put(e);
+        if (kWrite) writer->put(dlut_sym1(e));
         if (pos >= stop) {
             if (pos >= end_bit) r.term = kTermEnd;
             break;
@@ -247,8 +248,10 @@ struct WordWriter {
         pack = 0;
         room = out_room;
     }
+    // shifts in symbol 1 (kSecond = false) or symbol 2 (kSecond = true) of a LUT leaf entry
+    template <bool kSecond>
     __device__ __forceinline__ void put(uint32_t entry) {
-        pack = __byte_perm(pack, entry, 0x4321);  // shift in the symbol (low byte of the LUT entry)
+        pack = __byte_perm(pack, entry, kSecond ? 0x6321 : 0x5321);
         ++k;
         if ((k & 3u) == 0) {
             const uint32_t done = k - phase;  // symbols so far
@@ -294,18 +297,13 @@ __device__ __forceinline__ SpanS decode_smem(
     // fast region: at least 32 real bits follow `pos`, so a match can never lean on the zero fill and a
     // hole is an error straight away
     const uint32_t fast_end = (end >= 32u) ? min(stop, end - 31u) : 0u;
-    while (pos < fast_end) {
-        uint32_t e = s_lut[smem_window<kPadded>(s_in, pos) >> (32 - root_bits)];
-        if (e - 0x100u >= 0x7fffff00u) {  // not a plain leaf: link or hole
-            if ((int32_t)e < 0) {
-                const uint32_t window = smem_window<kPadded>(s_in, pos);
-                uint32_t used = root_bits;
-                do {
-                    const uint32_t width = (e >> 24) & 0x7fu;
-                    e = s_lut[(e & 0xFFFFFFu) + ((window << used) >> (32 - width))];
-                    used += width;
-                } while ((int32_t)e < 0);
-            }
+    // two symbols per lookup while even the second one is sure to start before `stop`
+    const uint32_t pair_end = fast_end > root_bits ? fast_end - root_bits : 0u;
+    while (pos < pair_end) {
+        const uint32_t window = smem_window<kPadded>(s_in, pos);
+        uint32_t e = s_lut[window >> (32 - root_bits)];
+        if (!dlut_is_leaf(e)) {  // link or hole (rare)
+            e = dec_walk(s_lut, root_bits, window, e);
             if (e == 0) {
                 if (kSkipHoles) {
                     ++pos;
@@ -315,9 +313,27 @@ __device__ __forceinline__ SpanS decode_smem(
                 break;
             }
         }
-        pos += e >> 8;
+        pos += dlut_total_len(e);
+        nsym += dlut_count(e);
+        if (kWrite) {
+            writer->template put<false>(e);
+            if (dlut_count(e) == 2) writer->template put<true>(e);
+        }
+    }
+    // one symbol per lookup up to the end of the fast region
+    while (term == kTermStop && pos < fast_end) {
+        const uint32_t e = dec_lookup(s_lut, root_bits, smem_window<kPadded>(s_in, pos));
+        if (e == 0) {
+            if (kSkipHoles) {
+                ++pos;
+                continue;
+            }
+            term = kTermUnknown;
+            break;
+        }
+        pos += dlut_len1(e);
         ++nsym;
-        if (kWrite) writer->put(e);
+        if (kWrite) writer->template put<false>(e);
     }
     if (term == kTermStop && pos < stop) {
         // fewer than 32 bits of stream remain: the window is the stream zero-extended
@@ -335,11 +351,11 @@ __device__ __forceinline__ SpanS decode_smem(
                 term = kTermEnd;  // fewer than 32 bits left: treated as padding (huffman.c:240-244)
                 break;
             }
-            const uint32_t used = e >> 8;
+            const uint32_t used = dlut_len1(e);
             if (used > left) { term = kTermEnd; break; }
             pos += used;
             ++nsym;
-            if (kWrite) writer->put(e);
+            if (kWrite) writer->template put<false>(e);
             if (pos >= stop) {
                 if (pos >= end) term = kTermEnd;
                 break;
@@ -357,11 +373,10 @@ __device__ __forceinline__ SpanS decode_smem(
 // ---------------------------------------------------------------------------------------------
 // Batch of independent strings
 // ---------------------------------------------------------------------------------------------
-constexpr int kDecThreads = 128;
+constexpr int kDecThreads = 256;
 constexpr int kDecWarps = kDecThreads / 32;
-constexpr int kDecItemsPerTile = 256;          // strings per tile
-constexpr int kDecGroups = kDecItemsPerTile / 32;
-constexpr uint32_t kDecStageWords = 8 * 1024;  // 32 KiB of encoded bytes per tile
+constexpr int kDecItemsPerTile = 384;           // strings per tile (12 groups of 32)
+constexpr uint32_t kDecStageWords = 11 * 1024;  // 44 KiB of encoded bytes per tile
 
 struct DecBatchArgs {
     BatchView b;
@@ -385,6 +400,7 @@ __global__ void __launch_bounds__(kDecThreads) decode_batch_kernel(DecBatchArgs 
     __shared__ uint32_t s_bytes[kDecItemsPerTile];  // encoded length
     __shared__ uint32_t s_cnt[kDecItemsPerTile];    // symbols per string, then exclusive offsets within the tile
     __shared__ uint16_t s_perm[kDecItemsPerTile];   // strings in order of decreasing length
+    static_assert(kDecItemsPerTile <= 2 * kDecThreads, "the block scan handles two strings per thread");
     __shared__ uint32_t s_hist[256];
     __shared__ uint64_t s_warp_sum[kDecWarps];
     __shared__ uint64_t s_prefix;
@@ -564,7 +580,7 @@ __global__ void __launch_bounds__(kDecThreads) decode_batch_kernel(DecBatchArgs 
 // ---------------------------------------------------------------------------------------------
 constexpr uint32_t kChunkBits = 1024;   // 128 encoded bytes per thread
 constexpr uint32_t kPrerollBits = 256;  // HPACK on Zipf data: 99.4 % of starts are in sync by then
-constexpr int kStreamThreads = 128;
+constexpr int kStreamThreads = 256;
 constexpr uint32_t kStreamRowWords = 33;                                      // 32 words + 1 copy of the next row's first
 constexpr uint32_t kStreamStageWords = (kStreamThreads + 1) * kStreamRowWords + 1;  // previous chunk + 128 own
 

@@ -13,9 +13,20 @@ constexpr int32_t kStatusUnknownSymbol = 3072;  // AWS_ERROR_COMPRESSION_UNKNOWN
 
 constexpr uint64_t kNoCap = ~0ull;  // "all the room it needs" (packed layout)
 
-// Device decode LUT entry (host/huffman_lut.h entries are re-encoded at context creation so the common
-// case needs one shift): leaf = len << 8 | symbol, link = 0x80000000 | width << 24 | base, hole = 0.
-constexpr uint32_t kDevLutLinkFlag = 0x80000000u;
+// Device decode LUT entry (host/huffman_lut.h entries are re-encoded at context creation):
+//   leaf : [31:24] bits consumed by the whole entry (1..32)   [23:16] symbol 2   [15:8] symbol 1
+//          [7:2] length of symbol 1's code   [1:0] symbols in the entry (1 or 2)
+//          Root entries hold TWO symbols whenever two complete codes fit in the root index; sub-table
+//          entries always hold one.
+//   link : [31:24] = 0, [23:20] index width of the sub-table (1..8), [19:0] its first entry
+//   hole : 0
+__device__ __forceinline__ bool dlut_is_leaf(uint32_t e) { return e >= 0x01000000u; }
+__device__ __forceinline__ uint32_t dlut_total_len(uint32_t e) { return e >> 24; }
+__device__ __forceinline__ uint32_t dlut_len1(uint32_t e) { return (e >> 2) & 63u; }
+__device__ __forceinline__ uint32_t dlut_sym1(uint32_t e) { return (e >> 8) & 0xffu; }
+__device__ __forceinline__ uint32_t dlut_count(uint32_t e) { return e & 3u; }
+__device__ __forceinline__ uint32_t dlut_link_width(uint32_t e) { return (e >> 20) & 0xfu; }
+__device__ __forceinline__ uint32_t dlut_link_base(uint32_t e) { return e & 0xFFFFFu; }
 
 // Device-resident tables of one context. Pointers are device pointers.
 struct DeviceTables {

@@ -178,12 +178,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) encode_items_warp_kernel(
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t lut_lookup(
     const uint32_t *s_lut, uint32_t s_count, const uint32_t *g_lut, uint32_t root_bits, uint32_t window) {
-    // device entry format: leaf = len << 8 | symbol, link = 0x80000000 | width << 24 | base, hole = 0
+    // returns a leaf entry (only its first symbol is used here) or 0 for a hole
     uint32_t e = s_lut[window >> (32 - root_bits)];
     uint32_t used = root_bits;
-    while ((int32_t)e < 0) {
-        const uint32_t width = (e >> 24) & 0x7fu;
-        const uint32_t idx = (e & 0xFFFFFFu) + ((window << used) >> (32 - width));
+    while (e != 0 && !dlut_is_leaf(e)) {
+        const uint32_t width = dlut_link_width(e);
+        const uint32_t idx = dlut_link_base(e) + ((window << used) >> (32 - width));
         e = idx < s_count ? s_lut[idx] : __ldg(&g_lut[idx]);
         used += width;
     }
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(256) decode_items_thread_kernel(DeviceTables t
             if (bits_left >= 32) status = kStatusUnknownSymbol;
             break;
         }
-        const uint32_t used = e >> 8;
+        const uint32_t used = dlut_len1(e);
         if (used > bits_left) break;
         if (out_len == C) {
             status = kStatusShortBuffer;
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(256) decode_items_thread_kernel(DeviceTables t
         bits_left -= used;
         reg <<= used;
         have -= used;
-        if (kWrite && out_len < phys_room) dst[out_len] = (uint8_t)e;
+        if (kWrite && out_len < phys_room) dst[out_len] = (uint8_t)dlut_sym1(e);
         ++out_len;
         if (bits_left == 0) break;
     }

@@ -90,7 +90,7 @@ struct aws_huffman_batch_ctx {
 
 namespace {
 
-constexpr uint32_t kLutRootBits = 10;
+constexpr uint32_t kLutRootBits = 12;
 constexpr uint32_t kLutSubBits = 8;
 constexpr uint32_t kLutMaxSmemEntries = 8192;  // 32 KiB
 
@@ -476,13 +476,33 @@ int aws_huffman_batch_ctx_new(
     HB_CTX_TRY(cudaMalloc(&ctx->d_lut, (size_t)lut.count * sizeof(uint32_t)));
     HB_CTX_TRY(cudaMemcpy(ctx->d_enc, enc, sizeof(enc), cudaMemcpyHostToDevice));
     {
-        // re-encode for the device: leaf = len << 8 | symbol, link = 0x80000000 | width << 24 | base
+        // re-encode for the device (format: device_common.cuh); root entries get a second symbol when
+        // two complete codes fit in the root index
         std::vector<uint32_t> dev(lut.count);
+        auto single = [](uint32_t len, uint32_t sym) { return (len << 24) | (sym << 8) | (len << 2) | 1u; };
         for (uint32_t i = 0; i < lut.count; ++i) {
             const uint32_t e = lut.entries[i];
             if (e == 0) dev[i] = 0;
-            else if (HUFFMAN_LUT_IS_LEAF(e)) dev[i] = ((uint32_t)HUFFMAN_LUT_LEAF_LEN(e) << 8) | HUFFMAN_LUT_LEAF_SYMBOL(e);
-            else dev[i] = hb::kDevLutLinkFlag | (HUFFMAN_LUT_LINK_WIDTH(e) << 24) | HUFFMAN_LUT_LINK_BASE(e);
+            else if (HUFFMAN_LUT_IS_LEAF(e)) dev[i] = single(HUFFMAN_LUT_LEAF_LEN(e), HUFFMAN_LUT_LEAF_SYMBOL(e));
+            else dev[i] = (HUFFMAN_LUT_LINK_WIDTH(e) << 20) | HUFFMAN_LUT_LINK_BASE(e);
+        }
+        if (lut.count >= (1u << 20)) {
+            huffman_lut_clean_up(&lut);
+            aws_huffman_batch_ctx_destroy(ctx);
+            return aws_raise_error(AWS_ERROR_COMPRESSION_INVALID_CODE_TABLE);
+        }
+        for (uint32_t i = 0; i < (1u << lut.root_bits); ++i) {
+            const uint32_t e = lut.entries[i];
+            if (!HUFFMAN_LUT_IS_LEAF(e)) continue;
+            const uint32_t len1 = HUFFMAN_LUT_LEAF_LEN(e);
+            if (len1 >= lut.root_bits) continue;
+            const uint32_t rest = lut.root_bits - len1;  // index bits left after the first code
+            const uint32_t window2 = (i << (32 - lut.root_bits)) << len1;
+            uint8_t sym2 = 0;
+            const uint8_t len2 = huffman_lut_decode(&lut, window2, &sym2);
+            if (len2 != 0 && len2 <= rest)
+                dev[i] = ((len1 + len2) << 24) | ((uint32_t)sym2 << 16) | ((uint32_t)HUFFMAN_LUT_LEAF_SYMBOL(e) << 8) |
+                         (len1 << 2) | 2u;
         }
         HB_CTX_TRY(cudaMemcpy(ctx->d_lut, dev.data(), (size_t)lut.count * sizeof(uint32_t), cudaMemcpyHostToDevice));
     }
