@@ -314,7 +314,7 @@ class BatchContext:
             raise CodecError(self.library.last_error(), fn_name)
 
     # ---- host-buffer entry points (numpy in, numpy out) ----
-    def _host(self, encode, data, in_offsets, out_capacity, out_offsets=None, out_caps=None, out=None):
+    def _host(self, encode, data, in_offsets, out_capacity, out_offsets=None, out_caps=None, out=None, extras=True):
         data = np.ascontiguousarray(data, dtype=np.uint8)
         in_offsets = np.ascontiguousarray(in_offsets, dtype=np.uint64)
         n = len(in_offsets) - 1
@@ -327,7 +327,9 @@ class BatchContext:
             "status": np.zeros(n, dtype=np.int32),
             "consumed": np.zeros(n, dtype=np.uint64),
         }
-        if encode:
+        if not extras:  # only payload, offsets and status (what a throughput-minded caller asks for)
+            del res["out_lens"], res["consumed"]
+        elif encode:
             res["overflow_pattern"] = np.zeros(n, dtype=np.uint32)
             res["overflow_num_bits"] = np.zeros(n, dtype=np.uint8)
         else:

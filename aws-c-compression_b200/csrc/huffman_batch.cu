@@ -68,8 +68,40 @@ struct GrowBuf {
         return static_cast<T *>(ptr);
     }
 };
+// Per-launch kernel scratch (tile descriptors, chunk records, ...). One per concurrent stream.
+struct Scratch {
+    GrowBuf lens, tile_state, tile_first, chunks, chunk_lens, chunk_offsets;
+    void release() {
+        GrowBuf *all[] = {&lens, &tile_state, &tile_first, &chunks, &chunk_lens, &chunk_offsets};
+        for (GrowBuf *g : all) g->release();
+    }
+};
+
+constexpr int kLanes = 3;
+struct Lane {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t kernels_done = nullptr, retired = nullptr;
+    bool in_flight = false;
+    uint64_t *h_total = nullptr;  // pinned: the sub-batch's output size
+    Scratch scratch;
+    GrowBuf in, in_off, out, out_off, lens, status, consumed, aux32, aux8, aux64;
+    void release() {
+        GrowBuf *all[] = {&in, &in_off, &out, &out_off, &lens, &status, &consumed, &aux32, &aux8, &aux64};
+        for (GrowBuf *g : all) g->release();
+        scratch.release();
+        if (h_total) cudaFreeHost(h_total);
+        if (kernels_done) cudaEventDestroy(kernels_done);
+        if (retired) cudaEventDestroy(retired);
+        if (stream) cudaStreamDestroy(stream);
+        h_total = nullptr;
+        kernels_done = retired = nullptr;
+        stream = nullptr;
+    }
+};
 }  // namespace hb_host
 using hb_host::GrowBuf;
+using hb_host::Lane;
+using hb_host::Scratch;
 
 struct aws_huffman_batch_ctx {
     int device = 0;
@@ -80,8 +112,12 @@ struct aws_huffman_batch_ctx {
     uint32_t lut_smem_entries = 0;
     uint64_t launches = 0;
 
-    // scratch for the device entry points
-    GrowBuf lens, tile_state, tile_first, chunks, chunk_lens, chunk_offsets;
+    // kernel scratch for the device entry points (and the simple host path)
+    hb_host::Scratch scratch;
+    // pipelined host path: independent lanes (stream + scratch + staging) so that the H2D copy of one
+    // sub-batch, the kernels of the next and the D2H copy of the previous one overlap
+    hb_host::Lane lanes[hb_host::kLanes];
+    cudaEvent_t offsets_ready = nullptr;
     int sm_count = 148;
     // staging for the host entry points
     GrowBuf s_in, s_in_off, s_out, s_out_off, s_caps, s_status, s_consumed, s_ovf_pattern, s_ovf_bits, s_left_bits,
@@ -121,12 +157,13 @@ hb::BatchView make_view(const aws_huffman_batch *b) {
 }
 
 // lens -> offsets on the device
-int launch_scan(aws_huffman_batch_ctx *ctx, const uint64_t *lens, uint64_t *offsets, uint64_t n, cudaStream_t stream) {
+int launch_scan(
+    aws_huffman_batch_ctx *ctx, Scratch &sc, const uint64_t *lens, uint64_t *offsets, uint64_t n, cudaStream_t stream) {
     const uint64_t tiles = std::max<uint64_t>(1, (n + kScanTile - 1) / kScanTile);
     const size_t state_bytes = tiles * sizeof(uint64_t) + 256;
-    HB_CUDA_TRY(ctx->tile_state.reserve(state_bytes));
-    HB_CUDA_TRY(cudaMemsetAsync(ctx->tile_state.ptr, 0, state_bytes, stream));
-    uint64_t *state = ctx->tile_state.as<uint64_t>();
+    HB_CUDA_TRY(sc.tile_state.reserve(state_bytes));
+    HB_CUDA_TRY(cudaMemsetAsync(sc.tile_state.ptr, 0, state_bytes, stream));
+    uint64_t *state = sc.tile_state.as<uint64_t>();
     uint32_t *ticket = reinterpret_cast<uint32_t *>(state + tiles);
     scan_lens_kernel<<<(unsigned)tiles, kScanThreads, 0, stream>>>(lens, offsets, n, state, ticket);
     ++ctx->launches;
@@ -135,12 +172,13 @@ int launch_scan(aws_huffman_batch_ctx *ctx, const uint64_t *lens, uint64_t *offs
 }
 
 // Packed layout, every symbol has a code: the tiled symbol-parallel kernel.
-int encode_tiled_on_device(aws_huffman_batch_ctx *ctx, const hb::BatchView &v, uint64_t total_in, cudaStream_t stream) {
+int encode_tiled_on_device(
+    aws_huffman_batch_ctx *ctx, Scratch &sc, const hb::BatchView &v, uint64_t total_in, cudaStream_t stream) {
     const uint64_t num_tiles = (total_in + kEncTile - 1) / kEncTile;
     const bool seg = v.n > 1;
     const size_t state_bytes = num_tiles * sizeof(uint64_t) + 256;
-    HB_CUDA_TRY(ctx->tile_state.reserve(state_bytes));
-    HB_CUDA_TRY(cudaMemsetAsync(ctx->tile_state.ptr, 0, state_bytes, stream));
+    HB_CUDA_TRY(sc.tile_state.reserve(state_bytes));
+    HB_CUDA_TRY(cudaMemsetAsync(sc.tile_state.ptr, 0, state_bytes, stream));
     EncTiledArgs a{};
     a.in = v.in;
     a.in_offsets = v.in_offsets;
@@ -149,15 +187,15 @@ int encode_tiled_on_device(aws_huffman_batch_ctx *ctx, const hb::BatchView &v, u
     a.out = v.out;
     a.out_capacity = v.out_capacity;
     a.out_offsets = v.out_offsets;
-    a.tile_state = ctx->tile_state.as<uint64_t>();
+    a.tile_state = sc.tile_state.as<uint64_t>();
     a.ticket = reinterpret_cast<uint32_t *>(a.tile_state + num_tiles);
     a.num_tiles = (uint32_t)num_tiles;
     a.eos_padding = ctx->tables.eos_padding;
     if (seg) {
-        HB_CUDA_TRY(ctx->tile_first.reserve((num_tiles + 1) * sizeof(uint32_t)));
-        a.tile_first = ctx->tile_first.as<uint32_t>();
+        HB_CUDA_TRY(sc.tile_first.reserve((num_tiles + 1) * sizeof(uint32_t)));
+        a.tile_first = sc.tile_first.as<uint32_t>();
         tile_index_kernel<<<(unsigned)((num_tiles + 1 + 255) / 256), 256, 0, stream>>>(
-            v.in_offsets, v.n, total_in, num_tiles, ctx->tile_first.as<uint32_t>());
+            v.in_offsets, v.n, total_in, num_tiles, sc.tile_first.as<uint32_t>());
         ++ctx->launches;
         encode_tiled_kernel<true><<<(unsigned)num_tiles, kEncThreads, kEncSmemBytes, stream>>>(ctx->tables.enc, a);
     } else {
@@ -175,23 +213,24 @@ int encode_tiled_on_device(aws_huffman_batch_ctx *ctx, const hb::BatchView &v, u
     return AWS_OP_SUCCESS;
 }
 
-int encode_on_device(aws_huffman_batch_ctx *ctx, hb::BatchView v, uint64_t total_in, cudaStream_t stream) {
+int encode_on_device(
+    aws_huffman_batch_ctx *ctx, Scratch &sc, hb::BatchView v, uint64_t total_in, cudaStream_t stream) {
     if (v.n == 0) return AWS_OP_SUCCESS;
     const bool force_generic = getenv("AWS_HUFFMAN_BATCH_FORCE_GENERIC") != nullptr;
     if (!v.out_caps && !ctx->tables.has_unknown && total_in > 0 && v.n < 0xffffffffull &&
         (total_in + kEncTile - 1) / kEncTile < 0xffffffffull && !force_generic) {
-        return encode_tiled_on_device(ctx, v, total_in, stream);
+        return encode_tiled_on_device(ctx, sc, v, total_in, stream);
     }
     if (!v.out_lens) {
-        HB_CUDA_TRY(ctx->lens.reserve(v.n * sizeof(uint64_t)));
-        v.out_lens = ctx->lens.as<uint64_t>();
+        HB_CUDA_TRY(sc.lens.reserve(v.n * sizeof(uint64_t)));
+        v.out_lens = sc.lens.as<uint64_t>();
     }
     const unsigned blocks = (unsigned)((v.n + kWarpsPerBlock - 1) / kWarpsPerBlock);
     if (!v.out_caps) {
         encode_items_warp_kernel<false><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(ctx->tables, v);
         ++ctx->launches;
         HB_CUDA_TRY(cudaGetLastError());
-        if (launch_scan(ctx, v.out_lens, v.out_offsets, v.n, stream)) return AWS_OP_ERR;
+        if (launch_scan(ctx, sc, v.out_lens, v.out_offsets, v.n, stream)) return AWS_OP_ERR;
     }
     encode_items_warp_kernel<true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(ctx->tables, v);
     ++ctx->launches;
@@ -200,17 +239,17 @@ int encode_on_device(aws_huffman_batch_ctx *ctx, hb::BatchView v, uint64_t total
 }
 
 // Packed layout, many strings: fused count -> look-back -> write kernel (one thread per string).
-int decode_batch_fast(aws_huffman_batch_ctx *ctx, const hb::BatchView &v, cudaStream_t stream) {
+int decode_batch_fast(aws_huffman_batch_ctx *ctx, Scratch &sc, const hb::BatchView &v, cudaStream_t stream) {
     const uint64_t num_tiles = (v.n + kDecItemsPerTile - 1) / kDecItemsPerTile;
     const size_t state_bytes = num_tiles * sizeof(uint64_t) + 256;
-    HB_CUDA_TRY(ctx->tile_state.reserve(state_bytes));
-    HB_CUDA_TRY(cudaMemsetAsync(ctx->tile_state.ptr, 0, state_bytes, stream));
+    HB_CUDA_TRY(sc.tile_state.reserve(state_bytes));
+    HB_CUDA_TRY(cudaMemsetAsync(sc.tile_state.ptr, 0, state_bytes, stream));
     DecBatchArgs a{};
     a.b = v;
     a.lut = ctx->tables.lut;
     a.lut_count = ctx->tables.lut_count;
     a.root_bits = ctx->tables.lut_root_bits;
-    a.tile_state = ctx->tile_state.as<uint64_t>();
+    a.tile_state = sc.tile_state.as<uint64_t>();
     a.ticket = reinterpret_cast<uint32_t *>(a.tile_state + num_tiles);
     a.num_tiles = (uint32_t)num_tiles;
     const size_t smem = ((size_t)ctx->tables.lut_count + kDecStageWords + 2) * sizeof(uint32_t);
@@ -223,20 +262,21 @@ int decode_batch_fast(aws_huffman_batch_ctx *ctx, const hb::BatchView &v, cudaSt
 }
 
 // Packed layout, one long stream: chunked speculative decode.
-int decode_stream_fast(aws_huffman_batch_ctx *ctx, const hb::BatchView &v, uint64_t len, cudaStream_t stream) {
+int decode_stream_fast(
+    aws_huffman_batch_ctx *ctx, Scratch &sc, const hb::BatchView &v, uint64_t len, cudaStream_t stream) {
     const uint64_t lead = reinterpret_cast<uintptr_t>(v.in) & 3;
     const uint64_t end_bit = (lead + len) * 8;
     const uint64_t num_chunks = (end_bit + kChunkBits - 1) / kChunkBits;
-    HB_CUDA_TRY(ctx->chunks.reserve(num_chunks * sizeof(uint64_t) + 64));
-    HB_CUDA_TRY(ctx->chunk_lens.reserve(num_chunks * sizeof(uint64_t)));
-    HB_CUDA_TRY(ctx->chunk_offsets.reserve((num_chunks + 1) * sizeof(uint64_t)));
+    HB_CUDA_TRY(sc.chunks.reserve(num_chunks * sizeof(uint64_t) + 64));
+    HB_CUDA_TRY(sc.chunk_lens.reserve(num_chunks * sizeof(uint64_t)));
+    HB_CUDA_TRY(sc.chunk_offsets.reserve((num_chunks + 1) * sizeof(uint64_t)));
     StreamArgs a{};
     a.in_aligned = v.in - lead;
     a.begin_bit = lead * 8;
     a.end_bit = end_bit;
     a.num_chunks = num_chunks;
-    a.chunks = ctx->chunks.as<uint64_t>();
-    a.chunk_offsets = ctx->chunk_offsets.as<uint64_t>();
+    a.chunks = sc.chunks.as<uint64_t>();
+    a.chunk_offsets = sc.chunk_offsets.as<uint64_t>();
     a.control = a.chunks + num_chunks;  // two words after the records
     a.lut = ctx->tables.lut;
     a.lut_count = ctx->tables.lut_count;
@@ -253,10 +293,10 @@ int decode_stream_fast(aws_huffman_batch_ctx *ctx, const hb::BatchView &v, uint6
     for (int round = 0; round < 2; ++round) stream_fix_kernel<<<wide, kStreamThreads, smem, stream>>>(a);
     stream_verify_kernel<<<flat, 256, 0, stream>>>(a);
     stream_repair_kernel<<<1, 32, smem, stream>>>(a);
-    stream_counts_kernel<<<flat, 256, 0, stream>>>(a, ctx->chunk_lens.as<uint64_t>());
+    stream_counts_kernel<<<flat, 256, 0, stream>>>(a, sc.chunk_lens.as<uint64_t>());
     ctx->launches += 6;
     HB_CUDA_TRY(cudaGetLastError());
-    if (launch_scan(ctx, ctx->chunk_lens.as<uint64_t>(), a.chunk_offsets, num_chunks, stream)) return AWS_OP_ERR;
+    if (launch_scan(ctx, sc, sc.chunk_lens.as<uint64_t>(), a.chunk_offsets, num_chunks, stream)) return AWS_OP_ERR;
     stream_write_kernel<<<wide, kStreamThreads, smem_staged, stream>>>(a, v);
     ++ctx->launches;
     HB_CUDA_TRY(cudaGetLastError());
@@ -265,16 +305,17 @@ int decode_stream_fast(aws_huffman_batch_ctx *ctx, const hb::BatchView &v, uint6
 
 constexpr uint64_t kStreamMinBytes = 64 * 1024;  // shorter single items go through the batch kernel
 
-int decode_on_device(aws_huffman_batch_ctx *ctx, hb::BatchView v, uint64_t total_in, cudaStream_t stream) {
+int decode_on_device(
+    aws_huffman_batch_ctx *ctx, Scratch &sc, hb::BatchView v, uint64_t total_in, cudaStream_t stream) {
     if (v.n == 0) return AWS_OP_SUCCESS;
     const bool force_generic = getenv("AWS_HUFFMAN_BATCH_FORCE_GENERIC") != nullptr;
     if (!v.out_caps && ctx->tables.lut_count <= kDecLutMaxSmem && !force_generic) {
-        if (v.n == 1 && total_in >= kStreamMinBytes) return decode_stream_fast(ctx, v, total_in, stream);
-        return decode_batch_fast(ctx, v, stream);
+        if (v.n == 1 && total_in >= kStreamMinBytes) return decode_stream_fast(ctx, sc, v, total_in, stream);
+        return decode_batch_fast(ctx, sc, v, stream);
     }
     if (!v.out_lens) {
-        HB_CUDA_TRY(ctx->lens.reserve(v.n * sizeof(uint64_t)));
-        v.out_lens = ctx->lens.as<uint64_t>();
+        HB_CUDA_TRY(sc.lens.reserve(v.n * sizeof(uint64_t)));
+        v.out_lens = sc.lens.as<uint64_t>();
     }
     const unsigned threads = 256;
     const unsigned blocks = (unsigned)((v.n + threads - 1) / threads);
@@ -283,11 +324,164 @@ int decode_on_device(aws_huffman_batch_ctx *ctx, hb::BatchView v, uint64_t total
         decode_items_thread_kernel<false><<<blocks, threads, smem, stream>>>(ctx->tables, v, ctx->lut_smem_entries);
         ++ctx->launches;
         HB_CUDA_TRY(cudaGetLastError());
-        if (launch_scan(ctx, v.out_lens, v.out_offsets, v.n, stream)) return AWS_OP_ERR;
+        if (launch_scan(ctx, sc, v.out_lens, v.out_offsets, v.n, stream)) return AWS_OP_ERR;
     }
     decode_items_thread_kernel<true><<<blocks, threads, smem, stream>>>(ctx->tables, v, ctx->lut_smem_entries);
     ++ctx->launches;
     HB_CUDA_TRY(cudaGetLastError());
+    return AWS_OP_SUCCESS;
+}
+
+__global__ void rebase_offsets_kernel(const uint64_t *src, uint64_t count, uint64_t base, uint64_t *dst) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) dst[i] = src[i] - base;
+}
+
+int lane_prepare(Lane &lane) {
+    if (lane.stream) return AWS_OP_SUCCESS;
+    HB_CUDA_TRY(cudaStreamCreateWithFlags(&lane.stream, cudaStreamNonBlocking));
+    HB_CUDA_TRY(cudaEventCreateWithFlags(&lane.kernels_done, cudaEventDisableTiming));
+    HB_CUDA_TRY(cudaEventCreateWithFlags(&lane.retired, cudaEventDisableTiming));
+    HB_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&lane.h_total), sizeof(uint64_t), cudaHostAllocDefault));
+    return AWS_OP_SUCCESS;
+}
+
+constexpr uint64_t kPipelineMinBytes = 8ull << 20;   // below this one shot is as good
+constexpr uint64_t kPipelineShardBytes = 16ull << 20;
+
+// Packed layout with many items: the batch is cut into sub-batches (contiguous item ranges balanced by
+// bytes) that flow through kLanes lanes, so the host->device copy of one sub-batch, the kernels of the
+// next and the device->host copy of the previous one run at the same time. Sub-batches are ordinary
+// independent batches on the device; their packed offsets are rebased on the host at the end
+// (the same concatenation step as multi-GPU sharding).
+int run_host_batch_pipelined(aws_huffman_batch_ctx *ctx, const aws_huffman_batch *b, bool encode) {
+    const size_t n = b->n;
+    const uint64_t total_in = b->in_offsets[n];
+    size_t shards = (size_t)std::min<uint64_t>(64, std::max<uint64_t>(2, total_in / kPipelineShardBytes));
+    shards = std::min(shards, n);
+    std::vector<size_t> begin(shards + 1);
+    if (aws_huffman_batch_plan_shards(b->in_offsets, n, shards, begin.data())) return AWS_OP_ERR;
+    std::vector<uint64_t> shard_base(shards + 1, 0);
+
+    for (Lane &lane : ctx->lanes)
+        if (lane_prepare(lane)) return AWS_OP_ERR;
+    if (!ctx->offsets_ready) HB_CUDA_TRY(cudaEventCreateWithFlags(&ctx->offsets_ready, cudaEventDisableTiming));
+
+    // all input offsets go up once; sub-batches rebase their slice on the device
+    HB_CUDA_TRY(ctx->s_in_off.reserve((n + 1) * sizeof(uint64_t)));
+    HB_CUDA_TRY(cudaMemcpyAsync(
+        ctx->s_in_off.ptr, b->in_offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    HB_CUDA_TRY(cudaEventRecord(ctx->offsets_ready, ctx->stream));
+
+    const uint32_t max_len = std::max<uint32_t>(1, ctx->tables.max_len);
+    const uint32_t min_len = std::max<uint32_t>(1, ctx->tables.min_len);
+    uint64_t base_out = 0;
+    bool overflow = false;
+
+    auto issue = [&](size_t j) -> int {
+        Lane &lane = ctx->lanes[j % hb_host::kLanes];
+        if (lane.in_flight) {
+            HB_CUDA_TRY(cudaEventSynchronize(lane.retired));
+            lane.in_flight = false;
+        }
+        const size_t a = begin[j], nj = begin[j + 1] - a;
+        const uint64_t in0 = b->in_offsets[a], bytes_in = b->in_offsets[a + nj] - in0;
+        const uint64_t room = encode ? bytes_in * ((max_len + 7) / 8) + 64 : (bytes_in * 8) / min_len + 64;
+        HB_CUDA_TRY(lane.in.reserve(bytes_in + 64));
+        HB_CUDA_TRY(lane.in_off.reserve((nj + 1) * sizeof(uint64_t)));
+        HB_CUDA_TRY(lane.out.reserve(room + 64));
+        HB_CUDA_TRY(lane.out_off.reserve((nj + 1) * sizeof(uint64_t)));
+        if (b->out_lens) HB_CUDA_TRY(lane.lens.reserve(nj * sizeof(uint64_t)));
+        if (b->status) HB_CUDA_TRY(lane.status.reserve(nj * sizeof(int32_t)));
+        if (b->consumed) HB_CUDA_TRY(lane.consumed.reserve(nj * sizeof(uint64_t)));
+        if (encode ? b->overflow_pattern != nullptr : false) HB_CUDA_TRY(lane.aux32.reserve(nj * sizeof(uint32_t)));
+        if (encode ? b->overflow_num_bits != nullptr : b->leftover_num_bits != nullptr) HB_CUDA_TRY(lane.aux8.reserve(nj));
+        if (!encode && b->leftover_working_bits) HB_CUDA_TRY(lane.aux64.reserve(nj * sizeof(uint64_t)));
+
+        HB_CUDA_TRY(cudaStreamWaitEvent(lane.stream, ctx->offsets_ready, 0));
+        if (bytes_in)
+            HB_CUDA_TRY(cudaMemcpyAsync(lane.in.ptr, b->in + in0, bytes_in, cudaMemcpyHostToDevice, lane.stream));
+        rebase_offsets_kernel<<<(unsigned)((nj + 1 + 255) / 256), 256, 0, lane.stream>>>(
+            ctx->s_in_off.as<uint64_t>() + a, nj + 1, in0, lane.in_off.as<uint64_t>());
+        ++ctx->launches;
+        hb::BatchView v{};
+        v.n = nj;
+        v.in = lane.in.as<uint8_t>();
+        v.in_offsets = lane.in_off.as<uint64_t>();
+        v.out = lane.out.as<uint8_t>();
+        v.out_capacity = room;
+        v.out_offsets = lane.out_off.as<uint64_t>();
+        v.out_lens = b->out_lens ? lane.lens.as<uint64_t>() : nullptr;
+        v.status = b->status ? lane.status.as<int32_t>() : nullptr;
+        v.consumed = b->consumed ? lane.consumed.as<uint64_t>() : nullptr;
+        if (encode) {
+            v.overflow_pattern = b->overflow_pattern ? lane.aux32.as<uint32_t>() : nullptr;
+            v.overflow_num_bits = b->overflow_num_bits ? lane.aux8.as<uint8_t>() : nullptr;
+        } else {
+            v.leftover_working_bits = b->leftover_working_bits ? lane.aux64.as<uint64_t>() : nullptr;
+            v.leftover_num_bits = b->leftover_num_bits ? lane.aux8.as<uint8_t>() : nullptr;
+        }
+        if ((encode ? encode_on_device(ctx, lane.scratch, v, bytes_in, lane.stream)
+                    : decode_on_device(ctx, lane.scratch, v, bytes_in, lane.stream)) != AWS_OP_SUCCESS)
+            return AWS_OP_ERR;
+        HB_CUDA_TRY(cudaMemcpyAsync(
+            lane.h_total, lane.out_off.as<uint64_t>() + nj, sizeof(uint64_t), cudaMemcpyDeviceToHost, lane.stream));
+        HB_CUDA_TRY(cudaEventRecord(lane.kernels_done, lane.stream));
+        lane.in_flight = true;
+        return AWS_OP_SUCCESS;
+    };
+
+    auto retire = [&](size_t j) -> int {
+        Lane &lane = ctx->lanes[j % hb_host::kLanes];
+        const size_t a = begin[j], nj = begin[j + 1] - a;
+        HB_CUDA_TRY(cudaEventSynchronize(lane.kernels_done));
+        const uint64_t total = *lane.h_total;
+        shard_base[j] = base_out;
+        cudaStream_t st = lane.stream;
+        if (base_out + total > b->out_capacity) overflow = true;
+        if (!overflow && total)
+            HB_CUDA_TRY(cudaMemcpyAsync(b->out + base_out, lane.out.ptr, total, cudaMemcpyDeviceToHost, st));
+        HB_CUDA_TRY(cudaMemcpyAsync(b->out_offsets + a, lane.out_off.ptr, nj * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        if (b->out_lens)
+            HB_CUDA_TRY(cudaMemcpyAsync(b->out_lens + a, lane.lens.ptr, nj * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        if (b->status)
+            HB_CUDA_TRY(cudaMemcpyAsync(b->status + a, lane.status.ptr, nj * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        if (b->consumed)
+            HB_CUDA_TRY(cudaMemcpyAsync(b->consumed + a, lane.consumed.ptr, nj * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        if (encode) {
+            if (b->overflow_pattern)
+                HB_CUDA_TRY(cudaMemcpyAsync(b->overflow_pattern + a, lane.aux32.ptr, nj * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            if (b->overflow_num_bits)
+                HB_CUDA_TRY(cudaMemcpyAsync(b->overflow_num_bits + a, lane.aux8.ptr, nj, cudaMemcpyDeviceToHost, st));
+        } else {
+            if (b->leftover_working_bits)
+                HB_CUDA_TRY(cudaMemcpyAsync(b->leftover_working_bits + a, lane.aux64.ptr, nj * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+            if (b->leftover_num_bits)
+                HB_CUDA_TRY(cudaMemcpyAsync(b->leftover_num_bits + a, lane.aux8.ptr, nj, cudaMemcpyDeviceToHost, st));
+        }
+        HB_CUDA_TRY(cudaEventRecord(lane.retired, st));
+        base_out += total;
+        return AWS_OP_SUCCESS;
+    };
+
+    const size_t depth = hb_host::kLanes - 1;  // sub-batches in flight ahead of the one being retired
+    for (size_t j = 0; j < shards + depth; ++j) {
+        if (j < shards && issue(j)) return AWS_OP_ERR;
+        if (j >= depth && retire(j - depth)) return AWS_OP_ERR;
+    }
+    for (Lane &lane : ctx->lanes) {
+        if (lane.in_flight) HB_CUDA_TRY(cudaEventSynchronize(lane.retired));
+        lane.in_flight = false;
+    }
+    // host-side concatenation: shard-local packed offsets -> global
+    for (size_t j = 0; j < shards; ++j) {
+        const uint64_t base = shard_base[j];
+        if (base == 0) continue;
+        uint64_t *o = b->out_offsets;
+        for (size_t i = begin[j]; i < begin[j + 1]; ++i) o[i] += base;
+    }
+    b->out_offsets[n] = base_out;
+    if (overflow) return aws_raise_error(AWS_ERROR_SHORT_BUFFER);
     return AWS_OP_SUCCESS;
 }
 
@@ -305,12 +499,14 @@ int run_host_batch(aws_huffman_batch_ctx *ctx, const aws_huffman_batch *b, bool 
     const uint64_t total_in = b->in_offsets[n];
     const bool slotted = b->out_caps != nullptr;
     if ((total_in && !b->in) || (b->out_capacity && !b->out)) return aws_raise_error(AWS_ERROR_INVALID_ARGUMENT);
+    if (!slotted && n >= 2 && total_in >= kPipelineMinBytes && !getenv("AWS_HUFFMAN_BATCH_NO_PIPELINE"))
+        return run_host_batch_pipelined(ctx, b, encode);
 
     HB_CUDA_TRY(ctx->s_in.reserve(total_in + 16));
     HB_CUDA_TRY(ctx->s_in_off.reserve((n + 1) * sizeof(uint64_t)));
     HB_CUDA_TRY(ctx->s_out.reserve(b->out_capacity + 16));
     HB_CUDA_TRY(ctx->s_out_off.reserve((n + 1) * sizeof(uint64_t)));
-    HB_CUDA_TRY(ctx->lens.reserve(n * sizeof(uint64_t)));
+    HB_CUDA_TRY(ctx->scratch.lens.reserve(n * sizeof(uint64_t)));
     if (slotted) HB_CUDA_TRY(ctx->s_caps.reserve(n * sizeof(uint64_t)));
     if (b->status) HB_CUDA_TRY(ctx->s_status.reserve(n * sizeof(int32_t)));
     if (b->consumed) HB_CUDA_TRY(ctx->s_consumed.reserve(n * sizeof(uint64_t)));
@@ -337,7 +533,7 @@ int run_host_batch(aws_huffman_batch_ctx *ctx, const aws_huffman_batch *b, bool 
     v.out_capacity = b->out_capacity;
     v.out_offsets = ctx->s_out_off.as<uint64_t>();
     v.out_caps = slotted ? ctx->s_caps.as<uint64_t>() : nullptr;
-    v.out_lens = ctx->lens.as<uint64_t>();
+    v.out_lens = ctx->scratch.lens.as<uint64_t>();
     v.status = b->status ? ctx->s_status.as<int32_t>() : nullptr;
     v.consumed = b->consumed ? ctx->s_consumed.as<uint64_t>() : nullptr;
     if (encode) {
@@ -348,12 +544,13 @@ int run_host_batch(aws_huffman_batch_ctx *ctx, const aws_huffman_batch *b, bool 
         v.leftover_num_bits = b->leftover_num_bits ? ctx->s_left_num.as<uint8_t>() : nullptr;
     }
 
-    v.out_lens = b->out_lens ? ctx->lens.as<uint64_t>() : nullptr;
-    if ((encode ? encode_on_device(ctx, v, total_in, st) : decode_on_device(ctx, v, total_in, st)) != AWS_OP_SUCCESS)
+    v.out_lens = b->out_lens ? ctx->scratch.lens.as<uint64_t>() : nullptr;
+    if ((encode ? encode_on_device(ctx, ctx->scratch, v, total_in, st)
+                : decode_on_device(ctx, ctx->scratch, v, total_in, st)) != AWS_OP_SUCCESS)
         return AWS_OP_ERR;
 
     if (b->out_lens)
-        HB_CUDA_TRY(cudaMemcpyAsync(b->out_lens, ctx->lens.ptr, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        HB_CUDA_TRY(cudaMemcpyAsync(b->out_lens, ctx->scratch.lens.ptr, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     if (b->status) HB_CUDA_TRY(cudaMemcpyAsync(b->status, v.status, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     if (b->consumed)
         HB_CUDA_TRY(cudaMemcpyAsync(b->consumed, v.consumed, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
@@ -538,11 +735,13 @@ void aws_huffman_batch_ctx_destroy(struct aws_huffman_batch_ctx *ctx) {
     }
     if (ctx->d_enc) cudaFree(ctx->d_enc);
     if (ctx->d_lut) cudaFree(ctx->d_lut);
-    GrowBuf *bufs[] = {&ctx->lens,     &ctx->tile_state, &ctx->tile_first, &ctx->chunks, &ctx->chunk_lens,
-                       &ctx->chunk_offsets, &ctx->s_in,       &ctx->s_in_off,      &ctx->s_out,
-                       &ctx->s_out_off, &ctx->s_caps,     &ctx->s_status,   &ctx->s_consumed,    &ctx->s_ovf_pattern,
-                       &ctx->s_ovf_bits, &ctx->s_left_bits, &ctx->s_left_num};
+    GrowBuf *bufs[] = {&ctx->s_in,       &ctx->s_in_off,      &ctx->s_out,      &ctx->s_out_off,
+                       &ctx->s_caps,     &ctx->s_status,      &ctx->s_consumed, &ctx->s_ovf_pattern,
+                       &ctx->s_ovf_bits, &ctx->s_left_bits,   &ctx->s_left_num};
     for (GrowBuf *g : bufs) g->release();
+    ctx->scratch.release();
+    for (Lane &lane : ctx->lanes) lane.release();
+    if (ctx->offsets_ready) cudaEventDestroy(ctx->offsets_ready);
     (void)cudaGetLastError();
     delete ctx;
 }
@@ -563,7 +762,7 @@ int aws_huffman_encode_batch_device(
     if (check_batch(batch)) return AWS_OP_ERR;
     HB_CUDA_TRY(cudaSetDevice(ctx->device));
     cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
-    return encode_on_device(ctx, make_view(batch), batch->in_size, st);
+    return encode_on_device(ctx, ctx->scratch, make_view(batch), batch->in_size, st);
 }
 
 int aws_huffman_decode_batch_device(
@@ -574,7 +773,7 @@ int aws_huffman_decode_batch_device(
     if (check_batch(batch)) return AWS_OP_ERR;
     HB_CUDA_TRY(cudaSetDevice(ctx->device));
     cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
-    return decode_on_device(ctx, make_view(batch), batch->in_size, st);
+    return decode_on_device(ctx, ctx->scratch, make_view(batch), batch->in_size, st);
 }
 
 int aws_huffman_get_encoded_length_batch(
@@ -591,15 +790,15 @@ int aws_huffman_get_encoded_length_batch(
     if (total_in && !in) return aws_raise_error(AWS_ERROR_INVALID_ARGUMENT);
     HB_CUDA_TRY(ctx->s_in.reserve(total_in + 16));
     HB_CUDA_TRY(ctx->s_in_off.reserve((n + 1) * sizeof(uint64_t)));
-    HB_CUDA_TRY(ctx->lens.reserve(n * sizeof(uint64_t)));
+    HB_CUDA_TRY(ctx->scratch.lens.reserve(n * sizeof(uint64_t)));
     if (total_in) HB_CUDA_TRY(cudaMemcpyAsync(ctx->s_in.ptr, in, total_in, cudaMemcpyHostToDevice, st));
     HB_CUDA_TRY(cudaMemcpyAsync(ctx->s_in_off.ptr, in_offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     const unsigned blocks = (unsigned)((n + kWarpsPerBlock - 1) / kWarpsPerBlock);
     encoded_length_kernel<<<blocks, kWarpsPerBlock * 32, 0, st>>>(
-        ctx->tables, ctx->s_in.as<uint8_t>(), ctx->s_in_off.as<uint64_t>(), n, ctx->lens.as<uint64_t>());
+        ctx->tables, ctx->s_in.as<uint8_t>(), ctx->s_in_off.as<uint64_t>(), n, ctx->scratch.lens.as<uint64_t>());
     ++ctx->launches;
     HB_CUDA_TRY(cudaGetLastError());
-    HB_CUDA_TRY(cudaMemcpyAsync(lens, ctx->lens.ptr, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    HB_CUDA_TRY(cudaMemcpyAsync(lens, ctx->scratch.lens.ptr, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     HB_CUDA_TRY(cudaStreamSynchronize(st));
     return AWS_OP_SUCCESS;
 }

@@ -365,16 +365,26 @@ def main():
 
     # ---- e2e through the host-pointer C ABI, pinned host buffers, copies inside the timed region
     e2e_steps = max(1, min(args.steps, 5))
+
+    def pinned(count, dtype):
+        return torch.empty(count, dtype=dtype).pin_memory().numpy()
+
     h_raw = raw.cpu().pin_memory().numpy()
     h_in_off = in_off.cpu().to(torch.int64).pin_memory().numpy().view(np.uint64)
-    h_enc = torch.empty(enc_cap, dtype=torch.uint8).pin_memory().numpy()
-    h_dec = torch.empty(raw_bytes + 1024, dtype=torch.uint8).pin_memory().numpy()
+    h_enc = pinned(enc_cap, torch.uint8)
+    h_enc_off = pinned(n + 1, torch.int64).view(np.uint64)
+    h_dec = pinned(raw_bytes + 1024, torch.uint8)
+    h_dec_off = pinned(n + 1, torch.int64).view(np.uint64)
+    h_status = pinned(n, torch.int32)
 
     def e2e_step():
-        r = ctx.encode(h_raw, h_in_off, enc_cap, out=h_enc)
-        total = int(r["out_offsets"][-1])
-        d = ctx.decode(h_enc[:total], r["out_offsets"], raw_bytes + 1024, out=h_dec)
-        return total, int(d["out_offsets"][-1])
+        # the call a user of the C ABI makes: aws_huffman_encode_batch / aws_huffman_decode_batch on host memory
+        ctx._call("aws_huffman_encode_batch", n, {"in_": h_raw, "in_offsets": h_in_off, "out": h_enc,
+                                                  "out_offsets": h_enc_off, "status": h_status}, enc_cap)
+        total = int(h_enc_off[n])
+        ctx._call("aws_huffman_decode_batch", n, {"in_": h_enc, "in_offsets": h_enc_off, "out": h_dec,
+                                                  "out_offsets": h_dec_off, "status": h_status}, raw_bytes + 1024)
+        return total, int(h_dec_off[n])
 
     e2e_step()
     torch.cuda.synchronize(device)
@@ -387,6 +397,7 @@ def main():
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     assert total == enc_bytes and back == raw_bytes
     assert np.array_equal(h_dec[:raw_bytes], h_raw), "e2e round trip mismatch"
+    assert not h_status.any()
 
     if sampler_proc is not None:
         sampler_proc.terminate()
@@ -425,7 +436,7 @@ def main():
                          "encode_frac": enc_gbs / peak, "decode_frac": dec_gbs / peak},
             "e2e": {"value": all_bytes / (e2e_ms * 1e-3) / 1e9, "unit": "GB/s",
                     "h2d_bytes_per_step": int(raw_bytes + 8 * (n + 1) + enc_bytes + 8 * (n + 1)),
-                    "d2h_bytes_per_step": int(enc_bytes + raw_bytes + 2 * 8 * (n + 1) + 2 * 28 * n),
+                    "d2h_bytes_per_step": int(enc_bytes + raw_bytes + 2 * 8 * (n + 1) + 2 * 4 * n),
                     "ms_per_step": e2e_ms, "steps": e2e_steps},
             "gpu_launches": int(all_launches),
             "clocks": summarize_clocks(clock_file),

@@ -407,3 +407,26 @@ def test_stream_that_never_self_synchronises(pkg, oracle):
         got_d = ctx.decode(stream, want["out_offsets"], 2 * n + 64)
         assert_same_packed(got_d, want_d)
     ctx.close()
+
+
+def test_pipelined_host_path(contexts, oracle, oracle_tables, pkg):
+    """Host entry points with a batch big enough (>= 8 MB) to be cut into overlapping sub-batches: results
+    must be identical to one shot, including the call-level SHORT_BUFFER with complete offsets."""
+    rng = np.random.default_rng(0x91E)
+    ctx, table = contexts("hpack"), oracle_tables["hpack"]
+    data, offs = refcodec.random_batch(rng, 300_000, 0, 256, "hpack")
+    assert len(data) > 34 << 20
+    cap = 2 * len(data)
+    want = oracle.encode_batch(table, 0xFF, data, offs, cap)
+    got = ctx.encode(data, offs, cap)
+    assert_same_packed(got, want)
+    total = int(want["out_offsets"][-1])
+    stream = want["out"][:total]
+    want_d = oracle.decode_batch(table, stream, want["out_offsets"], len(data) + 64)
+    got_d = ctx.decode(stream, want["out_offsets"], len(data) + 64)
+    assert_same_packed(got_d, want_d)
+    lean = ctx.encode(data, offs, cap, extras=False)
+    assert np.array_equal(lean["out_offsets"], want["out_offsets"]) and np.array_equal(lean["out"][:total], stream)
+    with pytest.raises(pkg.CodecError) as err:
+        ctx.encode(data, offs, total - 1)
+    assert err.value.code == pkg.AWS_ERROR_SHORT_BUFFER
