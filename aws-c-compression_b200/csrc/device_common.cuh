@@ -119,9 +119,11 @@ __device__ __forceinline__ uint64_t lookback_exclusive_prefix(uint64_t *tile_sta
         const int64_t idx = look - (int64_t)lane;
         uint64_t word = (kLbPrefix << kLbFlagShift);  // lanes past tile 0 act as "prefix 0"
         if (idx >= 0) {
-            do {
+            while (true) {
                 word = ld_relaxed_u64(&tile_state[idx]);
-            } while ((word >> kLbFlagShift) == kLbInvalid);
+                if ((word >> kLbFlagShift) != kLbInvalid) break;
+                __nanosleep(20);
+            }
         }
         const uint32_t is_prefix = (word >> kLbFlagShift) == kLbPrefix;
         const uint32_t prefix_mask = __ballot_sync(0xffffffffu, is_prefix);

@@ -95,28 +95,49 @@ __device__ __forceinline__ void seg_publish_aggregate(uint64_t *tile_state, uint
 // tile by walking back to the nearest tile whose end position is known, then publishes this tile's
 // end position.
 __device__ __forceinline__ uint64_t seg_resolve(uint64_t *tile_state, uint32_t tile, const Seg &agg) {
+    // Every lane inspects kLbPerLane consecutive descriptors per round trip, so one window covers
+    // 32 * kLbPerLane tiles: with hundreds of tiles in flight the distance to the nearest resolved tile is
+    // a few hundred descriptors, and the number of dependent L2 round trips is what a tile waits for.
+    constexpr int kLbPerLane = 4;
     const uint32_t lane = lane_id();
     if (tile == 0) return 0;
     uint64_t G = 0;
     Seg64 acc = {0, 0, 0};  // function of tiles (look+1 .. tile-1), identity so far
     int64_t look = (int64_t)tile - 1;
     while (true) {
-        const int64_t idx = look - (int64_t)lane;
-        uint64_t word = kLbPrefix << kLbFlagShift;  // "tile -1" ends at bit 0
-        if (idx >= 0) {
-            do {
-                word = ld_relaxed_u64(&tile_state[idx]);
-            } while ((word >> kLbFlagShift) == kLbInvalid);
+        const int64_t base = look - (int64_t)lane * kLbPerLane;  // my closest descriptor; q steps further back
+        uint64_t word[kLbPerLane];
+#pragma unroll
+        for (int q = 0; q < kLbPerLane; ++q) {
+            const int64_t idx = base - q;
+            word[q] = kLbPrefix << kLbFlagShift;  // "tile -1" ends at bit 0
+            if (idx >= 0) {
+                while (true) {
+                    word[q] = ld_relaxed_u64(&tile_state[idx]);
+                    if ((word[q] >> kLbFlagShift) != kLbInvalid) break;
+                    __nanosleep(20);  // a spinning warp must not steal issue slots from the packing warps
+                }
+            }
         }
-        const bool is_prefix = (word >> kLbFlagShift) == kLbPrefix;
-        const uint32_t pmask = __ballot_sync(0xffffffffu, is_prefix);
-        const uint32_t first = pmask ? (uint32_t)(__ffs(pmask) - 1) : 32u;
+        // my function: descriptors closer than my first end position, composed earliest -> latest
+        int qp = kLbPerLane;
+#pragma unroll
+        for (int q = kLbPerLane - 1; q >= 0; --q)
+            if ((word[q] >> kLbFlagShift) == kLbPrefix) qp = q;
         Seg64 f = {0, 0, 0};
-        if (lane < first) {
-            f.hb = (uint32_t)(word >> 61) & 1u;
-            f.head = (word >> 31) & 0x3FFFFFFFull;
-            f.tail = word & 0x7FFFFFFFull;
+#pragma unroll
+        for (int q = kLbPerLane - 1; q >= 0; --q) {
+            if (q < qp) {
+                Seg64 d;
+                d.hb = (uint32_t)(word[q] >> 61) & 1u;
+                d.head = (word[q] >> 31) & 0x3FFFFFFFull;
+                d.tail = word[q] & 0x7FFFFFFFull;
+                f = seg_combine64(f, d);
+            }
         }
+        const uint32_t pmask = __ballot_sync(0xffffffffu, qp < kLbPerLane);
+        const uint32_t first = pmask ? (uint32_t)(__ffs(pmask) - 1) : 32u;
+        if (lane > first) f = Seg64{0, 0, 0};
         // ordered reduction: higher lanes hold EARLIER tiles
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -132,11 +153,15 @@ __device__ __forceinline__ uint64_t seg_resolve(uint64_t *tile_state, uint32_t t
         window.hb = __shfl_sync(0xffffffffu, f.hb, 0);
         acc = seg_combine64(window, acc);
         if (pmask) {
-            const uint64_t end_of_known = __shfl_sync(0xffffffffu, word & kLbValueMask, first);
+            uint64_t mine_end = 0;
+#pragma unroll
+            for (int q = 0; q < kLbPerLane; ++q)
+                if (q == qp) mine_end = word[q] & kLbValueMask;
+            const uint64_t end_of_known = __shfl_sync(0xffffffffu, mine_end, first);
             G = seg_apply64(acc, end_of_known);
             break;
         }
-        look -= 32;
+        look -= 32 * kLbPerLane;
     }
     if (lane == 0) st_relaxed_u64(&tile_state[tile], (kLbPrefix << kLbFlagShift) | (seg_apply(agg, G) & kLbValueMask));
     return G;
@@ -170,6 +195,7 @@ struct EncTiledArgs {
     uint32_t *ticket;
     uint32_t num_tiles;
     uint32_t eos_padding;
+    uint32_t debug;  // timing experiments only (AWS_HUFFMAN_BATCH_EXPERIMENT); results are wrong when set
 };
 
 // Appends one code to a right-aligned 64-bit accumulator; whenever 32 bits are complete they go to the
@@ -187,24 +213,27 @@ struct EncTiledArgs {
         nbm |= ~31;                                                                                                    \
     } while (0)
 
-// kSeg : items may start inside the tile (n > 1)
-// kFull: the tile holds exactly kEncTile symbols (everything but the last tile of the input)
-template <bool kSeg, bool kFull>
-__device__ __forceinline__ void encode_tile(
-    const uint2 *__restrict__ enc_table, const EncTiledArgs &a, uint32_t tile, uint2 *s_tab, uint32_t *s_mask,
-    uint32_t *s_first_item, Seg *s_warp, uint64_t *s_pos, uint32_t *s_slot, uint16_t *s_runbits, uint32_t *s_stage) {
+// One look-back descriptor covers a MACRO tile of kEncSub consecutive tiles: the chain of dependent
+// L2 round trips a block waits for is paid once per 16 KiB of input instead of once per 4 KiB.
+constexpr int kEncSub = 4;
+constexpr int kEncMaskWords = kEncSub * kEncTile / 32;
 
-    const uint32_t tid = threadIdx.x;
-    const uint32_t lane = tid & 31, warp = tid >> 5;
-    const uint64_t t0 = (uint64_t)tile * kEncTile;
-    const uint64_t t1 = kFull ? t0 + kEncTile : a.total_in;
-    const uint64_t p0 = t0 + (uint64_t)tid * kEncSymsPerThread;
-    const uint32_t nsym = kFull ? (uint32_t)kEncSymsPerThread
-                                : (p0 >= t1 ? 0u : (uint32_t)min((uint64_t)kEncSymsPerThread, t1 - p0));
+struct EncShared {
+    const uint2 *tab;      // [256] code table
+    uint32_t *mask;        // [kEncMaskWords] item-start bits of the macro tile
+    Seg *warp;             // [kEncThreads / 32]
+    Seg *totals;           // [kEncSub] function of each tile of the macro tile
+    uint64_t *pos;         // [1] absolute bit position of the macro tile
+    uint32_t *stage;       // staging buffer of one tile's output
+    uint32_t *slot;        // private packed words
+    uint16_t *runbits;     // bit counts of finished runs
+    uint16_t *obpos;       // stage byte where the item starting at a given symbol begins
+};
 
-    // ---- load 16 symbols -------------------------------------------------------------------------
-    uint32_t w[4] = {0, 0, 0, 0};
-    if (nsym == kEncSymsPerThread && ((reinterpret_cast<uintptr_t>(a.in) & 15) == 0)) {
+template <bool kFull>
+__device__ __forceinline__ void enc_load_symbols(const EncTiledArgs &a, uint64_t p0, uint32_t nsym, uint32_t (&w)[4]) {
+    w[0] = w[1] = w[2] = w[3] = 0;
+    if (kFull && ((reinterpret_cast<uintptr_t>(a.in) & 15) == 0)) {
         const uint4 v = __ldg(reinterpret_cast<const uint4 *>(a.in + p0));
         w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
     } else {
@@ -212,23 +241,22 @@ __device__ __forceinline__ void encode_tile(
         for (int k = 0; k < kEncSymsPerThread; ++k)
             if ((uint32_t)k < nsym) w[k >> 2] |= (uint32_t)a.in[p0 + k] << (8 * (k & 3));
     }
+}
 
-    // ---- item starts inside the tile ------------------------------------------------------------------
-    uint32_t end_in_tile = 0;
-    uint32_t m = 0;
-    if (kSeg) {
-        const uint32_t first_in_tile = a.tile_first[tile];
-        end_in_tile = a.tile_first[tile + 1];
-        for (uint32_t i = first_in_tile + tid; i < end_in_tile; i += kEncThreads) {
-            const uint32_t p = (uint32_t)(a.in_offsets[i] - t0);
-            atomicOr(&s_mask[p >> 5], 1u << (p & 31));
-            atomicMin(&s_first_item[p >> 4], i);
-        }
-        __syncthreads();
-        m = (s_mask[tid >> 1] >> ((tid & 1) * 16)) & 0xffffu;
-    }
+// Phases A + B of one tile: code lengths -> my segment function -> block scan. Returns my exclusive
+// function from the start of the tile; the tile's own function lands in sh.totals[sub].
+template <bool kSeg, bool kFull>
+__device__ __forceinline__ Seg enc_tile_measure(const EncTiledArgs &a, const EncShared &sh, uint32_t tile, uint32_t sub, uint32_t m) {
+    const uint32_t tid = threadIdx.x;
+    const uint32_t lane = tid & 31, warp = tid >> 5;
+    const uint64_t t0 = (uint64_t)tile * kEncTile;
+    const uint64_t t1 = kFull ? t0 + kEncTile : a.total_in;
+    const uint64_t p0 = t0 + (uint64_t)tid * kEncSymsPerThread;
+    const uint32_t nsym = kFull ? (uint32_t)kEncSymsPerThread
+                                : (p0 >= t1 ? 0u : (uint32_t)min((uint64_t)kEncSymsPerThread, t1 - p0));
+    uint32_t w[4];
+    enc_load_symbols<kFull>(a, p0, nsym, w);
 
-    // ---- A: code lengths only -> my segment function (cheap; lets the tile publish early) ---------------
     Seg mine = {0, 0, 0};
     {
         uint32_t run = 0;
@@ -241,12 +269,11 @@ __device__ __forceinline__ void encode_tile(
                 run = 0;
             }
             const uint32_t sym = (w[k >> 2] >> (8 * (k & 3))) & 0xffu;
-            run += s_tab[sym].y;
+            run += sh.tab[sym].y;
         }
         if (mine.hb) mine.tail += run; else mine.head = run;
     }
 
-    // ---- B: block scan of segment functions; publish the tile's function right away -----------------------
     Seg incl = mine;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -255,12 +282,12 @@ __device__ __forceinline__ void encode_tile(
     }
     Seg excl = seg_shfl_up(incl, 1);
     if (lane == 0) excl = Seg{0, 0, 0};
-    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();  // sh.warp free again
+    if (lane == 31) sh.warp[warp] = incl;
     __syncthreads();
-    Seg total;
     {
         // every warp redoes the 8-entry scan (cheaper than another barrier)
-        Seg wv = lane < kEncThreads / 32 ? s_warp[lane] : Seg{0, 0, 0};
+        Seg wv = lane < kEncThreads / 32 ? sh.warp[lane] : Seg{0, 0, 0};
         Seg wi = wv;
 #pragma unroll
         for (int d = 1; d < kEncThreads / 32; d <<= 1) {
@@ -269,6 +296,7 @@ __device__ __forceinline__ void encode_tile(
         }
         Seg we = seg_shfl_up(wi, 1);
         if (lane == 0) we = Seg{0, 0, 0};
+        Seg total;
         total.head = __shfl_sync(0xffffffffu, wi.head, kEncThreads / 32 - 1);
         total.tail = __shfl_sync(0xffffffffu, wi.tail, kEncThreads / 32 - 1);
         total.hb = __shfl_sync(0xffffffffu, wi.hb, kEncThreads / 32 - 1);
@@ -277,17 +305,31 @@ __device__ __forceinline__ void encode_tile(
         mywarp.tail = __shfl_sync(0xffffffffu, we.tail, warp);
         mywarp.hb = __shfl_sync(0xffffffffu, we.hb, warp);
         excl = seg_combine(mywarp, excl);  // my exclusive function from the start of the tile
+        if (tid == 0) sh.totals[sub] = total;
     }
-    if (tid == 0) seg_publish_aggregate(a.tile_state, tile, total);
+    return excl;
+}
 
-    // ---- C: pack my symbols into my private slot, run by run (position independent) ------------------------
-    // A "run" is a maximal stretch of my symbols inside one item. Runs are packed left-aligned, each
-    // starting on a fresh slot word; finished runs leave their bit count in s_runbits[run][tid].
+// Phase C of one tile: pack my symbols into my private slot, run by run (position independent).
+// A "run" is a maximal stretch of my symbols inside one item. Runs are packed left-aligned, each
+// starting on a fresh slot word; finished runs leave their bit count in runbits[run][tid].
+template <bool kSeg, bool kFull>
+__device__ __forceinline__ void enc_tile_pack(
+    const EncTiledArgs &a, const EncShared &sh, uint32_t tile, uint32_t m, uint32_t &runs_done, uint32_t &last_bits) {
+    const uint32_t tid = threadIdx.x;
+    const uint64_t t0 = (uint64_t)tile * kEncTile;
+    const uint64_t t1 = kFull ? t0 + kEncTile : a.total_in;
+    const uint64_t p0 = t0 + (uint64_t)tid * kEncSymsPerThread;
+    const uint32_t nsym = kFull ? (uint32_t)kEncSymsPerThread
+                                : (p0 >= t1 ? 0u : (uint32_t)min((uint64_t)kEncSymsPerThread, t1 - p0));
+    uint32_t w[4];
+    enc_load_symbols<kFull>(a, p0, nsym, w);
+
     uint64_t acc = 0;
     int nbm = -32;
-    uint32_t *sp = s_slot + tid;
+    uint32_t *sp = sh.slot + tid;
     uint32_t *run_begin = sp;
-    uint32_t runs_done = 0;
+    runs_done = 0;
 #pragma unroll
     for (int k = 0; k < kEncSymsPerThread; ++k) {
         if (!kFull && (uint32_t)k >= nsym) break;
@@ -299,34 +341,32 @@ __device__ __forceinline__ void encode_tile(
                 *sp = (uint32_t)(acc << (32 - rem));
                 sp += kEncThreads;
             }
-            s_runbits[runs_done * kEncThreads + tid] = (uint16_t)bits;
+            sh.runbits[runs_done * kEncThreads + tid] = (uint16_t)bits;
             ++runs_done;
             run_begin = sp;
             acc = 0;
             nbm = -32;
         }
         const uint32_t sym = (w[k >> 2] >> (8 * (k & 3))) & 0xffu;
-        const uint2 e = s_tab[sym];
+        const uint2 e = sh.tab[sym];
         HB_ENC_APPEND(e.x, e.y);
     }
-    uint32_t last_bits;
-    {
-        const uint32_t rem = (uint32_t)(nbm + 32);
-        last_bits = (uint32_t)(sp - run_begin) / kEncThreads * 32u + rem;
-        if (rem) *sp = (uint32_t)(acc << (32 - rem));
-    }
+    const uint32_t rem = (uint32_t)(nbm + 32);
+    last_bits = (uint32_t)(sp - run_begin) / kEncThreads * 32u + rem;
+    if (rem) *sp = (uint32_t)(acc << (32 - rem));
+}
 
-    // ---- D: resolve the tile's absolute position (predecessors published long ago) -------------------------
-    if (warp == 0) {
-        const uint64_t G0 = seg_resolve(a.tile_state, tile, total);
-        if (lane == 0) {
-            s_pos[0] = G0;
-            s_pos[1] = seg_apply(total, G0);
-        }
-    }
-    __syncthreads();
-
-    const uint64_t G = s_pos[0], Gend = s_pos[1];
+// Phases E.. of one tile whose absolute bit range [G, Gend) is known: shift-copy my packed runs into
+// the stage, complete the last byte, copy the owned bytes out, record item start offsets, re-zero.
+// Requires a block barrier between enc_tile_pack and this call.
+template <bool kSeg, bool kFull>
+__device__ __forceinline__ void enc_tile_emit(
+    const EncTiledArgs &a, const EncShared &sh, uint32_t tile, uint32_t m, const Seg &excl, uint64_t G, uint64_t Gend,
+    uint32_t runs_done, uint32_t last_bits) {
+    const uint32_t tid = threadIdx.x;
+    const uint64_t t0 = (uint64_t)tile * kEncTile;
+    const uint64_t t1 = kFull ? t0 + kEncTile : a.total_in;
+    uint32_t *s_stage = sh.stage;
     const uint64_t P = seg_apply(excl, G);  // absolute bit position of my first code
 
     // Staging origin: stage byte 0 <-> global address (out + G/8) rounded down to 16 bytes.
@@ -334,15 +374,13 @@ __device__ __forceinline__ void encode_tile(
     const uint32_t misalign = (uint32_t)((reinterpret_cast<uintptr_t>(a.out) + g_byte0) & 15);
     const int64_t origin_byte = (int64_t)g_byte0 - (int64_t)misalign;  // absolute output byte of stage byte 0
 
-    // ---- 3: shift-copy my runs from the slot to their bit positions in the stage ------------------------------
     {
         uint32_t D = (uint32_t)((int64_t)P - origin_byte * 8);  // stage bit index of the current run
-        const uint32_t *src = s_slot + tid;
-        uint32_t cur_item = kSeg ? s_first_item[tid] : 0u;
+        const uint32_t *src = sh.slot + tid;
         uint32_t boundary_bits = m;
         const uint32_t num_runs = runs_done + 1;
         for (uint32_t r = 0; r < num_runs; ++r) {
-            const uint32_t bits = (r + 1 == num_runs) ? last_bits : (uint32_t)s_runbits[r * kEncThreads + tid];
+            const uint32_t bits = (r + 1 == num_runs) ? last_bits : (uint32_t)sh.runbits[r * kEncThreads + tid];
             if (kSeg && r > 0) {
                 // byte-align: pad the item that just ended with the LOW bits of eos_padding
                 // (reference huffman.c:178-184), then note where the new item starts
@@ -354,22 +392,17 @@ __device__ __forceinline__ void encode_tile(
                 }
                 const uint32_t k = (uint32_t)__ffs(boundary_bits) - 1;
                 boundary_bits &= boundary_bits - 1;
-                const uint64_t here = p0 + k;
-                const uint64_t ob = (uint64_t)(origin_byte + (int64_t)(D >> 3));
-                do {
-                    a.out_offsets[cur_item] = ob;
-                    ++cur_item;
-                } while (cur_item < a.n && a.in_offsets[cur_item] == here);
+                sh.obpos[tid * kEncSymsPerThread + k] = (uint16_t)(D >> 3);  // stage byte where the item starts
             }
             if (bits) {
-                const uint32_t sh = D & 31;
+                const uint32_t shift = D & 31;
                 uint32_t *dst = s_stage + (D >> 5);
                 const uint32_t nsrc = (bits + 31) >> 5;
-                const uint32_t ndst = (sh + bits + 31) >> 5;
+                const uint32_t ndst = (shift + bits + 31) >> 5;
                 uint32_t prev = 0;
                 for (uint32_t j = 0; j < ndst; ++j) {
                     const uint32_t cur = j < nsrc ? src[j * kEncThreads] : 0u;
-                    const uint32_t word = __byte_perm(__funnelshift_r(cur, prev, sh), 0, 0x0123);
+                    const uint32_t word = __byte_perm(__funnelshift_r(cur, prev, shift), 0, 0x0123);
                     if (j == 0 || j + 1 == ndst) atomicOr(dst + j, word); else dst[j] = word;
                     prev = cur;
                 }
@@ -380,6 +413,11 @@ __device__ __forceinline__ void encode_tile(
     }
 
     // ---- the bits that complete this tile's last byte ------------------------------------------------
+    uint32_t first_in_tile = 0, end_in_tile = 0;
+    if (kSeg) {
+        first_in_tile = a.tile_first[tile];
+        end_in_tile = a.tile_first[tile + 1];
+    }
     const bool last_tile = tile + 1 == a.num_tiles;
     if (tid == 0) {
         const uint32_t need = (8u - (uint32_t)(Gend & 7u)) & 7u;
@@ -388,7 +426,7 @@ __device__ __forceinline__ void encode_tile(
             if (kSeg && end_in_tile < a.n) stop = a.in_offsets[end_in_tile];
             uint32_t bits = 0, have = 0;
             for (uint64_t p = t1; have < need && p < stop; ++p) {
-                const uint2 e = s_tab[a.in[p]];
+                const uint2 e = sh.tab[a.in[p]];
                 const uint32_t take = min(e.y, need - have);
                 bits = (bits << take) | (e.x >> (e.y - take));
                 have += take;
@@ -412,7 +450,7 @@ __device__ __forceinline__ void encode_tile(
     }
     __syncthreads();
 
-    // ---- 4: copy the bytes this tile owns ------------------------------------------------------------------
+    // ---- copy the bytes this tile owns; item start offsets (coalesced) -----------------------------------
     {
         const uint64_t own_lo = (G + 7) >> 3, own_hi = min((Gend + 7) >> 3, a.out_capacity);
         if (own_hi > own_lo) {
@@ -431,43 +469,131 @@ __device__ __forceinline__ void encode_tile(
                 for (uint32_t i = s_lo + tid; i < s_hi; i += kEncThreads) gbase[i] = sb[i];
             }
         }
+        if (kSeg) {
+            for (uint32_t i = first_in_tile + tid; i < end_in_tile; i += kEncThreads) {
+                const uint32_t p = (uint32_t)(a.in_offsets[i] - t0);
+                a.out_offsets[i] = (uint64_t)(origin_byte + (int64_t)sh.obpos[p]);
+            }
+        }
+    }
+    // the stage must be all zero again for the next tile: clear exactly what this tile touched
+    __syncthreads();
+    {
+        const uint32_t z_lo = (uint32_t)((int64_t)(G >> 3) - origin_byte) >> 4;
+        const uint32_t z_hi = ((uint32_t)((int64_t)((Gend + 7) >> 3) - origin_byte) + 15) >> 4;
+        uint4 *z = reinterpret_cast<uint4 *>(s_stage);
+        for (uint32_t i = z_lo + tid; i < z_hi; i += kEncThreads) z[i] = make_uint4(0, 0, 0, 0);
     }
 }
 
 constexpr int kEncSlotWords = kEncTile;  // 16 words per thread: every symbol fits one word
-constexpr size_t kEncSmemBytes = kEncSlotWords * 4 + kEncStageBytes + kEncTile * 2 /* runbits */;
+constexpr size_t kEncSmemBytes =
+    kEncSlotWords * 4 + kEncStageBytes + kEncTile * 2 /* runbits */ + kEncTile * 2 /* item start positions */;
 
+// Persistent blocks: the code table is loaded and the stage zeroed once; macro tiles come from an
+// atomic ticket taken only when the block is ready to start (a held-but-idle ticket would stall every
+// successor's look-back).
 template <bool kSeg>
 __global__ void __launch_bounds__(kEncThreads, 4) encode_tiled_kernel(const uint2 *__restrict__ enc_table, EncTiledArgs a) {
     __shared__ uint2 s_tab[256];
-    __shared__ uint32_t s_mask[kEncTile / 32];
-    __shared__ uint32_t s_first_item[kEncThreads];
+    __shared__ uint32_t s_mask[kEncMaskWords];
     __shared__ Seg s_warp[kEncThreads / 32];
-    __shared__ uint32_t s_tile;
-    __shared__ uint64_t s_pos[2];
+    __shared__ Seg s_totals[kEncSub];
+    __shared__ uint32_t s_ticket;
+    __shared__ uint64_t s_pos[1];
     extern __shared__ __align__(16) uint8_t s_dyn[];
-    uint32_t *s_stage = reinterpret_cast<uint32_t *>(s_dyn);
-    uint32_t *s_slot = reinterpret_cast<uint32_t *>(s_dyn + kEncStageBytes);
-    uint16_t *s_runbits = reinterpret_cast<uint16_t *>(s_dyn + kEncStageBytes + kEncSlotWords * 4);
+    EncShared sh;
+    sh.tab = s_tab;
+    sh.mask = s_mask;
+    sh.warp = s_warp;
+    sh.totals = s_totals;
+    sh.pos = s_pos;
+    sh.stage = reinterpret_cast<uint32_t *>(s_dyn);
+    sh.slot = reinterpret_cast<uint32_t *>(s_dyn + kEncStageBytes);
+    sh.runbits = reinterpret_cast<uint16_t *>(s_dyn + kEncStageBytes + kEncSlotWords * 4);
+    sh.obpos = sh.runbits + kEncTile;
 
     const uint32_t tid = threadIdx.x;
-    if (tid == 0) s_tile = atomicAdd(a.ticket, 1u);
+    const uint32_t num_macro = (a.num_tiles + kEncSub - 1) / kEncSub;
+    if (tid == 0) s_ticket = atomicAdd(a.ticket, 1u);
     s_tab[tid] = enc_table[tid];
-    if (kSeg) {
-        if (tid < kEncTile / 32) s_mask[tid] = 0;
-        s_first_item[tid] = 0xffffffffu;
-    }
     {
-        uint4 *z = reinterpret_cast<uint4 *>(s_stage);
+        uint4 *z = reinterpret_cast<uint4 *>(sh.stage);
         for (uint32_t i = tid; i < kEncStageBytes / 16; i += kEncThreads) z[i] = make_uint4(0, 0, 0, 0);
     }
     __syncthreads();
-    const uint32_t tile = s_tile;
-    const bool full = (uint64_t)(tile + 1) * kEncTile <= a.total_in;
-    if (full)
-        encode_tile<kSeg, true>(enc_table, a, tile, s_tab, s_mask, s_first_item, s_warp, s_pos, s_slot, s_runbits, s_stage);
-    else
-        encode_tile<kSeg, false>(enc_table, a, tile, s_tab, s_mask, s_first_item, s_warp, s_pos, s_slot, s_runbits, s_stage);
+    uint32_t macro = s_ticket;
+    while (macro < num_macro) {
+        const uint32_t tile0 = macro * kEncSub;
+        const uint32_t nsub = min((uint32_t)kEncSub, a.num_tiles - tile0);
+
+        // ---- item starts inside the macro tile -> one bit per symbol ----------------------------------------
+        uint32_t m[kEncSub];
+#pragma unroll
+        for (int s = 0; s < kEncSub; ++s) m[s] = 0;
+        if (kSeg) {
+            for (uint32_t i = tid; i < kEncMaskWords; i += kEncThreads) s_mask[i] = 0;
+            __syncthreads();
+            const uint64_t t0 = (uint64_t)tile0 * kEncTile;
+            const uint32_t first = a.tile_first[tile0], end = a.tile_first[tile0 + nsub];
+            for (uint32_t i = first + tid; i < end; i += kEncThreads) {
+                const uint32_t p = (uint32_t)(a.in_offsets[i] - t0);
+                atomicOr(&s_mask[p >> 5], 1u << (p & 31));
+            }
+            __syncthreads();
+#pragma unroll
+            for (int s = 0; s < kEncSub; ++s)
+                m[s] = (s_mask[s * (kEncTile / 32) + (tid >> 1)] >> ((tid & 1) * 16)) & 0xffffu;
+        }
+
+        // ---- A + B for every tile of the macro tile, then publish the macro tile's function ------------------
+        Seg excl[kEncSub];
+#pragma unroll
+        for (int s = 0; s < kEncSub; ++s) {
+            excl[s] = Seg{0, 0, 0};
+            if ((uint32_t)s < nsub) {
+                const uint32_t tile = tile0 + s;
+                const bool full = (uint64_t)(tile + 1) * kEncTile <= a.total_in;
+                excl[s] = full ? enc_tile_measure<kSeg, true>(a, sh, tile, s, m[s])
+                               : enc_tile_measure<kSeg, false>(a, sh, tile, s, m[s]);
+            }
+        }
+        __syncthreads();  // s_totals complete
+        Seg macro_total = s_totals[0];
+        for (uint32_t s = 1; s < nsub; ++s) macro_total = seg_combine(macro_total, s_totals[s]);
+        if (tid == 0) seg_publish_aggregate(a.tile_state, macro, macro_total);
+
+        // ---- C.. per tile; the macro tile's position is resolved after the first packing --------------------
+        uint64_t G = 0;
+#pragma unroll
+        for (int s = 0; s < kEncSub; ++s) {
+            if ((uint32_t)s < nsub) {
+                const uint32_t tile = tile0 + s;
+                const bool full = (uint64_t)(tile + 1) * kEncTile <= a.total_in;
+                uint32_t runs_done, last_bits;
+                if (full) enc_tile_pack<kSeg, true>(a, sh, tile, m[s], runs_done, last_bits);
+                else enc_tile_pack<kSeg, false>(a, sh, tile, m[s], runs_done, last_bits);
+                if (s == 0) {
+                    if (tid < 32) {
+                        const uint64_t G0 = (a.debug & 1u) ? (uint64_t)macro * kEncSub * kEncTile * 6
+                                                           : seg_resolve(a.tile_state, macro, macro_total);
+                        if (tid == 0) s_pos[0] = G0;
+                    }
+                    __syncthreads();
+                    G = s_pos[0];
+                } else {
+                    __syncthreads();  // the previous tile's stage clearing is complete
+                }
+                const uint64_t Gend = seg_apply(s_totals[s], G);
+                if (full) enc_tile_emit<kSeg, true>(a, sh, tile, m[s], excl[s], G, Gend, runs_done, last_bits);
+                else enc_tile_emit<kSeg, false>(a, sh, tile, m[s], excl[s], G, Gend, runs_done, last_bits);
+                G = Gend;
+            }
+        }
+        if (tid == 0) s_ticket = atomicAdd(a.ticket, 1u);
+        __syncthreads();
+        macro = s_ticket;
+    }
 }
 
 // Optional per-item arrays in the packed layout when no symbol can be unknown: every item succeeds.

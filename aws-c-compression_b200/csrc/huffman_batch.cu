@@ -191,15 +191,22 @@ int encode_tiled_on_device(
     a.ticket = reinterpret_cast<uint32_t *>(a.tile_state + num_tiles);
     a.num_tiles = (uint32_t)num_tiles;
     a.eos_padding = ctx->tables.eos_padding;
+    if (const char *exp = getenv("AWS_HUFFMAN_BATCH_EXPERIMENT")) a.debug = (uint32_t)atoi(exp);
+    const uint64_t num_macro = (num_tiles + kEncSub - 1) / kEncSub;  // one look-back descriptor each
+    const unsigned grid = (unsigned)std::min<uint64_t>(num_macro, (uint64_t)ctx->sm_count * 4);
     if (seg) {
         HB_CUDA_TRY(sc.tile_first.reserve((num_tiles + 1) * sizeof(uint32_t)));
         a.tile_first = sc.tile_first.as<uint32_t>();
         tile_index_kernel<<<(unsigned)((num_tiles + 1 + 255) / 256), 256, 0, stream>>>(
             v.in_offsets, v.n, total_in, num_tiles, sc.tile_first.as<uint32_t>());
         ++ctx->launches;
-        encode_tiled_kernel<true><<<(unsigned)num_tiles, kEncThreads, kEncSmemBytes, stream>>>(ctx->tables.enc, a);
+        HB_CUDA_TRY(cudaFuncSetAttribute(
+            encode_tiled_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEncSmemBytes));
+        encode_tiled_kernel<true><<<grid, kEncThreads, kEncSmemBytes, stream>>>(ctx->tables.enc, a);
     } else {
-        encode_tiled_kernel<false><<<(unsigned)num_tiles, kEncThreads, kEncSmemBytes, stream>>>(ctx->tables.enc, a);
+        HB_CUDA_TRY(cudaFuncSetAttribute(
+            encode_tiled_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEncSmemBytes));
+        encode_tiled_kernel<false><<<grid, kEncThreads, kEncSmemBytes, stream>>>(ctx->tables.enc, a);
     }
     ++ctx->launches;
     HB_CUDA_TRY(cudaGetLastError());
