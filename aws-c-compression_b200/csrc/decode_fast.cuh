@@ -297,13 +297,34 @@ __device__ __forceinline__ SpanS decode_smem(
     // fast region: at least 32 real bits follow `pos`, so a match can never lean on the zero fill and a
     // hole is an error straight away
     const uint32_t fast_end = (end >= 32u) ? min(stop, end - 31u) : 0u;
-    // two symbols per lookup while even the second one is sure to start before `stop`
+    // two symbols per lookup while even the second one is sure to start before `stop`.
+    // Codes longer than the root index (a few % of symbols) need a walk through sub-tables. Doing that
+    // walk the moment one lane needs it would make the other 31 lanes wait almost every iteration, so
+    // a lane that hits a link parks (`pending`) and parked lanes are resolved together every few steps.
     const uint32_t pair_end = fast_end > root_bits ? fast_end - root_bits : 0u;
+    constexpr int kStepsPerRound = 6;
+    bool pending = false;
     while (pos < pair_end) {
-        const uint32_t window = smem_window<kPadded>(s_in, pos);
-        uint32_t e = s_lut[window >> (32 - root_bits)];
-        if (!dlut_is_leaf(e)) {  // link or hole (rare)
-            e = dec_walk(s_lut, root_bits, window, e);
+#pragma unroll
+        for (int step = 0; step < kStepsPerRound; ++step) {
+            if (!pending && pos < pair_end) {
+                const uint32_t e = s_lut[smem_window<kPadded>(s_in, pos) >> (32 - root_bits)];
+                if (dlut_is_leaf(e)) {
+                    pos += dlut_total_len(e);
+                    nsym += dlut_count(e);
+                    if (kWrite) {
+                        writer->template put<false>(e);
+                        if (dlut_count(e) == 2) writer->template put<true>(e);
+                    }
+                } else {
+                    pending = true;
+                }
+            }
+        }
+        if (pending) {
+            pending = false;
+            const uint32_t window = smem_window<kPadded>(s_in, pos);
+            const uint32_t e = dec_walk(s_lut, root_bits, window, s_lut[window >> (32 - root_bits)]);
             if (e == 0) {
                 if (kSkipHoles) {
                     ++pos;
@@ -312,12 +333,9 @@ __device__ __forceinline__ SpanS decode_smem(
                 term = kTermUnknown;
                 break;
             }
-        }
-        pos += dlut_total_len(e);
-        nsym += dlut_count(e);
-        if (kWrite) {
-            writer->template put<false>(e);
-            if (dlut_count(e) == 2) writer->template put<true>(e);
+            pos += dlut_len1(e);
+            ++nsym;
+            if (kWrite) writer->template put<false>(e);
         }
     }
     // one symbol per lookup up to the end of the fast region
@@ -427,13 +445,24 @@ __global__ void __launch_bounds__(kDecThreads) decode_batch_kernel(DecBatchArgs 
         // ---- stage the tile's encoded bytes as big-endian words; histogram of string lengths -----------------
         const uint64_t byte0 = b.in_offsets[item0], byte1 = b.in_offsets[item0 + nitems];
         const uintptr_t addr0 = reinterpret_cast<uintptr_t>(b.in) + byte0;
-        const uint32_t lead = (uint32_t)(addr0 & 3);
+        const uint32_t lead = (uint32_t)(addr0 & 15);  // the stage starts on a 16-byte boundary
         const uint64_t nwords64 = (byte1 - byte0 + lead + 3) >> 2;
         const bool staged = nwords64 <= kDecStageWords;
         if (staged) {
             const uint32_t nwords = (uint32_t)nwords64;
+            const uint32_t nquads = nwords >> 2;  // whole 128-bit loads; the ragged end goes word by word
+            const uint4 *g4 = reinterpret_cast<const uint4 *>(addr0 - lead);
+            for (uint32_t j = threadIdx.x; j < nquads; j += kDecThreads) {
+                const uint4 v = __ldg(g4 + j);
+                uint32_t *dst = s_in + 4 * j;
+                dst[0] = __byte_perm(v.x, 0, 0x0123);
+                dst[1] = __byte_perm(v.y, 0, 0x0123);
+                dst[2] = __byte_perm(v.z, 0, 0x0123);
+                dst[3] = __byte_perm(v.w, 0, 0x0123);
+            }
             const uint32_t *gw = reinterpret_cast<const uint32_t *>(addr0 - lead);
-            for (uint32_t j = threadIdx.x; j < nwords; j += kDecThreads) s_in[j] = __byte_perm(__ldg(gw + j), 0, 0x0123);
+            for (uint32_t j = 4 * nquads + threadIdx.x; j < nwords; j += kDecThreads)
+                s_in[j] = __byte_perm(__ldg(gw + j), 0, 0x0123);
             if (threadIdx.x < 2) s_in[nwords + threadIdx.x] = 0;
         }
         for (uint32_t it = threadIdx.x; it < nitems; it += kDecThreads) {
@@ -574,7 +603,7 @@ __global__ void __launch_bounds__(kDecThreads) decode_batch_kernel(DecBatchArgs 
 // ---------------------------------------------------------------------------------------------
 // One long stream
 //
-// Positions are bits in "aligned space": bit 0 is the first bit of the 4-byte aligned word that holds
+// Positions are bits in "aligned space": bit 0 is the first bit of the 16-byte aligned block that holds
 // the stream's first byte, so chunk k is exactly the aligned words [32k, 32k + 32) and the stream
 // occupies [begin_bit, end_bit) = [8 * lead, 8 * (lead + len)).
 // ---------------------------------------------------------------------------------------------
@@ -599,7 +628,7 @@ __device__ __forceinline__ uint32_t chunk_nsym(uint64_t w) { return (uint32_t)((
 __device__ __forceinline__ uint32_t chunk_term(uint64_t w) { return (uint32_t)((w >> 48) & 3u); }
 
 struct StreamArgs {
-    const uint8_t *in_aligned;  // the stream's first byte, rounded down to 4 bytes
+    const uint8_t *in_aligned;  // the stream's first byte, rounded down to 16 bytes
     uint64_t begin_bit;         // 8 * lead
     uint64_t end_bit;           // 8 * (lead + len)
     uint64_t num_chunks;
@@ -622,24 +651,40 @@ __device__ __forceinline__ uint64_t decode_chunk_record(
     return chunk_pack(entry, exit, (uint32_t)r.nsym, r.term);
 }
 
-// Stages chunks [c0 - 1, c0 + 128] of the stream as big-endian words in the padded row layout and
-// zeroes everything outside [begin, end). Stage bit 0 is the first bit of chunk c0 - 1.
+// Stages chunks [c0 - 1, c0 + kStreamThreads] of the stream as big-endian words in the padded row
+// layout and zeroes everything outside the stream. Stage bit 0 is the first bit of chunk c0 - 1.
+// in_aligned is 16-byte aligned, so every chunk row is eight 128-bit loads.
+__device__ __forceinline__ uint32_t stream_be_word(uint32_t raw, int64_t w, uint64_t end_byte) {
+    // big-endian value of aligned word w, with the bytes past the end of the stream cleared
+    if (w < 0) return 0;
+    const uint64_t first_byte = (uint64_t)w * 4;
+    if (first_byte >= end_byte) return 0;
+    uint32_t v = __byte_perm(raw, 0, 0x0123);
+    if (first_byte + 4 > end_byte) v &= 0xffffffffu << (8 * (first_byte + 4 - end_byte));
+    return v;
+}
+
 __device__ __forceinline__ void stream_stage(const StreamArgs &a, uint64_t c0, uint32_t *s_in) {
-    const uint32_t *gw = reinterpret_cast<const uint32_t *>(a.in_aligned);
+    const uint4 *g4 = reinterpret_cast<const uint4 *>(a.in_aligned);
     const uint64_t end_byte = a.end_bit >> 3;
-    const uint64_t nwords_valid = (end_byte + 3) >> 2;
-    // rows 0..128 hold 32 words each; word 32 of a row duplicates word 0 of the next row
-    for (uint32_t i = threadIdx.x; i < (kStreamThreads + 1) * 32 + 1; i += kStreamThreads) {
-        const uint32_t row = i >> 5, col = i & 31;
-        const int64_t w = ((int64_t)c0 - 1 + row) * 32 + col;  // aligned word index in the stream
-        uint32_t v = 0;
-        if (w >= 0 && (uint64_t)w < nwords_valid) {
-            v = __byte_perm(__ldg(gw + w), 0, 0x0123);
-            const uint64_t first_byte = (uint64_t)w * 4;
-            if (first_byte + 4 > end_byte) v &= 0xffffffffu << (8 * (first_byte + 4 - end_byte));
+    const uint64_t nquads_valid = (end_byte + 15) >> 4;
+    // rows 0..kStreamThreads hold 32 words (8 quads) each; word 32 of a row duplicates word 0 of the next
+    constexpr uint32_t kQuads = (kStreamThreads + 1) * 8 + 1;
+    for (uint32_t i = threadIdx.x; i < kQuads; i += kStreamThreads) {
+        const uint32_t row = i >> 3, col4 = i & 7;
+        const int64_t q = ((int64_t)c0 - 1 + row) * 8 + col4;  // aligned 16-byte index in the stream
+        uint4 raw = make_uint4(0, 0, 0, 0);
+        if (q >= 0 && (uint64_t)q < nquads_valid) raw = __ldg(g4 + q);
+        const int64_t w = q * 4;
+        const uint32_t v0 = stream_be_word(raw.x, w, end_byte);
+        if (row <= kStreamThreads) {
+            uint32_t *dst = s_in + row * kStreamRowWords + col4 * 4;
+            dst[0] = v0;
+            dst[1] = stream_be_word(raw.y, w + 1, end_byte);
+            dst[2] = stream_be_word(raw.z, w + 2, end_byte);
+            dst[3] = stream_be_word(raw.w, w + 3, end_byte);
         }
-        if (row <= kStreamThreads) s_in[row * kStreamRowWords + col] = v;
-        if (col == 0 && row > 0) s_in[(row - 1) * kStreamRowWords + 32] = v;
+        if (col4 == 0 && row > 0) s_in[(row - 1) * kStreamRowWords + 32] = v0;
     }
 }
 

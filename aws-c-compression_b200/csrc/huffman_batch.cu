@@ -271,7 +271,7 @@ int decode_batch_fast(aws_huffman_batch_ctx *ctx, Scratch &sc, const hb::BatchVi
 // Packed layout, one long stream: chunked speculative decode.
 int decode_stream_fast(
     aws_huffman_batch_ctx *ctx, Scratch &sc, const hb::BatchView &v, uint64_t len, cudaStream_t stream) {
-    const uint64_t lead = reinterpret_cast<uintptr_t>(v.in) & 3;
+    const uint64_t lead = reinterpret_cast<uintptr_t>(v.in) & 15;  // "aligned space" starts on a 16-byte boundary
     const uint64_t end_bit = (lead + len) * 8;
     const uint64_t num_chunks = (end_bit + kChunkBits - 1) / kChunkBits;
     HB_CUDA_TRY(sc.chunks.reserve(num_chunks * sizeof(uint64_t) + 64));
