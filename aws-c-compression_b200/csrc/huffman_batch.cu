@@ -77,7 +77,7 @@ struct Scratch {
     }
 };
 
-constexpr int kLanes = 3;
+constexpr int kLanes = 5;
 struct Lane {
     cudaStream_t stream = nullptr;
     cudaEvent_t kernels_done = nullptr, retired = nullptr;
@@ -344,6 +344,11 @@ __global__ void rebase_offsets_kernel(const uint64_t *src, uint64_t count, uint6
     if (i < count) dst[i] = src[i] - base;
 }
 
+__global__ void add_base_kernel(uint64_t *offsets, uint64_t count, uint64_t base) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) offsets[i] += base;
+}
+
 int lane_prepare(Lane &lane) {
     if (lane.stream) return AWS_OP_SUCCESS;
     HB_CUDA_TRY(cudaStreamCreateWithFlags(&lane.stream, cudaStreamNonBlocking));
@@ -364,7 +369,9 @@ constexpr uint64_t kPipelineShardBytes = 16ull << 20;
 int run_host_batch_pipelined(aws_huffman_batch_ctx *ctx, const aws_huffman_batch *b, bool encode) {
     const size_t n = b->n;
     const uint64_t total_in = b->in_offsets[n];
-    size_t shards = (size_t)std::min<uint64_t>(64, std::max<uint64_t>(2, total_in / kPipelineShardBytes));
+    uint64_t shard_bytes = kPipelineShardBytes;
+    if (const char *mb = getenv("AWS_HUFFMAN_BATCH_SHARD_MB")) shard_bytes = std::max<uint64_t>(1, atoi(mb)) << 20;
+    size_t shards = (size_t)std::min<uint64_t>(256, std::max<uint64_t>(2, total_in / shard_bytes));
     shards = std::min(shards, n);
     std::vector<size_t> begin(shards + 1);
     if (aws_huffman_batch_plan_shards(b->in_offsets, n, shards, begin.data())) return AWS_OP_ERR;
@@ -448,6 +455,11 @@ int run_host_batch_pipelined(aws_huffman_batch_ctx *ctx, const aws_huffman_batch
         if (base_out + total > b->out_capacity) overflow = true;
         if (!overflow && total)
             HB_CUDA_TRY(cudaMemcpyAsync(b->out + base_out, lane.out.ptr, total, cudaMemcpyDeviceToHost, st));
+        if (base_out) {
+            // the concatenation step: shard-local packed offsets -> global, before they leave the device
+            add_base_kernel<<<(unsigned)((nj + 255) / 256), 256, 0, st>>>(lane.out_off.as<uint64_t>(), nj, base_out);
+            ++ctx->launches;
+        }
         HB_CUDA_TRY(cudaMemcpyAsync(b->out_offsets + a, lane.out_off.ptr, nj * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
         if (b->out_lens)
             HB_CUDA_TRY(cudaMemcpyAsync(b->out_lens + a, lane.lens.ptr, nj * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
@@ -471,7 +483,11 @@ int run_host_batch_pipelined(aws_huffman_batch_ctx *ctx, const aws_huffman_batch
         return AWS_OP_SUCCESS;
     };
 
-    const size_t depth = hb_host::kLanes - 1;  // sub-batches in flight ahead of the one being retired
+    // A sub-batch is retired (its D2H copies queued) two issues after it was issued; with more lanes than
+    // that, re-using a lane never has to wait for a D2H copy that is still running, so uploads of later
+    // sub-batches and downloads of earlier ones stay concurrent.
+    const size_t depth = 2;
+    static_assert(hb_host::kLanes > 3, "lanes must outnumber the issue-to-retire distance");
     for (size_t j = 0; j < shards + depth; ++j) {
         if (j < shards && issue(j)) return AWS_OP_ERR;
         if (j >= depth && retire(j - depth)) return AWS_OP_ERR;
@@ -479,13 +495,6 @@ int run_host_batch_pipelined(aws_huffman_batch_ctx *ctx, const aws_huffman_batch
     for (Lane &lane : ctx->lanes) {
         if (lane.in_flight) HB_CUDA_TRY(cudaEventSynchronize(lane.retired));
         lane.in_flight = false;
-    }
-    // host-side concatenation: shard-local packed offsets -> global
-    for (size_t j = 0; j < shards; ++j) {
-        const uint64_t base = shard_base[j];
-        if (base == 0) continue;
-        uint64_t *o = b->out_offsets;
-        for (size_t i = begin[j]; i < begin[j + 1]; ++i) o[i] += base;
     }
     b->out_offsets[n] = base_out;
     if (overflow) return aws_raise_error(AWS_ERROR_SHORT_BUFFER);
