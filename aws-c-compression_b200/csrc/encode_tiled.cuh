@@ -274,13 +274,35 @@ __device__ __forceinline__ Seg enc_tile_measure(const EncTiledArgs &a, const Enc
         if (mine.hb) mine.tail += run; else mine.head = run;
     }
 
+    Seg excl;
+    if (!kSeg) {
+        // a single stream has no item starts: plain prefix sums of bit counts
+        const uint32_t bits = mine.head;
+        const uint32_t incl = warp_inclusive_scan(bits);
+        uint32_t *warp_sums = reinterpret_cast<uint32_t *>(sh.warp);
+        __syncthreads();  // sh.warp free again
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        uint32_t wsum = lane < kEncThreads / 32 ? warp_sums[lane] : 0u;
+        uint32_t wincl = wsum;
+#pragma unroll
+        for (int d = 1; d < kEncThreads / 32; d <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, wincl, d);
+            if (lane >= (uint32_t)d) wincl += up;
+        }
+        const uint32_t total_bits = __shfl_sync(0xffffffffu, wincl, kEncThreads / 32 - 1);
+        const uint32_t before_my_warp = __shfl_sync(0xffffffffu, wincl - wsum, warp);
+        excl = Seg{before_my_warp + incl - bits, 0, 0};
+        if (tid == 0) sh.totals[sub] = Seg{total_bits, 0, 0};
+        return excl;
+    }
     Seg incl = mine;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const Seg up = seg_shfl_up(incl, d);
         if (lane >= (uint32_t)d) incl = seg_combine(up, incl);
     }
-    Seg excl = seg_shfl_up(incl, 1);
+    excl = seg_shfl_up(incl, 1);
     if (lane == 0) excl = Seg{0, 0, 0};
     __syncthreads();  // sh.warp free again
     if (lane == 31) sh.warp[warp] = incl;
