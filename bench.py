@@ -137,6 +137,22 @@ def summarize_clocks(path):
             "samples": len(sm)}
 
 
+def profiled_traffic(workload, dominant):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+    (profiles/r1_kernels.json, made by tools/ncu_summary.py), or None."""
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r1_kernels.json")))
+        group = prof["hpack_batch" if workload == "hpack_batch" else "stream_256MiB"]
+        want = {"encode": "encode_tiled", "decode": "decode_batch" if workload == "hpack_batch" else "stream_write"}[dominant]
+        for k in group:
+            if want in k["kernel"]:
+                scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
+                return int(k["dram_read"] * scale[k["dram_read_unit"]] + k["dram_write"] * scale[k["dram_write_unit"]])
+    except Exception:
+        pass
+    return None
+
+
 def measured_peak():
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -432,8 +448,14 @@ def main():
             "encode_gbs_per_gpu": enc_gbs, "decode_gbs_per_gpu": dec_gbs,
             "encode_ms": enc_ms_mean, "decode_ms": dec_ms_mean,
             "raw_bytes_per_gpu": raw_bytes, "encoded_bytes_per_gpu": enc_bytes,
-            "roofline": {"bound": "hbm", "kernel": dominant + " kernels (per GPU)", "achieved": achieved,
-                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm",
+                         "kernel": {"hpack_batch": {"encode": "encode_tiled_kernel<true>", "decode": "decode_batch_kernel"},
+                                    "stream": {"encode": "encode_tiled_kernel<false>",
+                                               "decode": "stream_sync_kernel + stream_write_kernel (+ small helpers)"}}
+                                   [args.workload][dominant] + " (per GPU; CUDA events around the " + dominant + " call)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": profiled_traffic(args.workload, dominant) if args.workload == "hpack_batch" else None,
+                         "algorithmic_bytes_per_launch": int(one_way),
                          "peak_source": peak_src, "frac_of_8000_nominal": achieved / 8000.0,
                          "encode_frac": enc_gbs / peak, "decode_frac": dec_gbs / peak},
             "e2e": {"value": all_bytes / (e2e_ms * 1e-3) / 1e9, "unit": "GB/s",
