@@ -119,6 +119,7 @@ struct aws_huffman_batch_ctx {
     hb_host::Lane lanes[hb_host::kLanes];
     cudaEvent_t offsets_ready = nullptr;
     int sm_count = 148;
+    int enc_blocks_per_sm[2] = {0, 0};  // resident blocks per SM of encode_tiled_kernel<seg>
     // staging for the host entry points
     GrowBuf s_in, s_in_off, s_out, s_out_off, s_caps, s_status, s_consumed, s_ovf_pattern, s_ovf_bits, s_left_bits,
         s_left_num;
@@ -192,22 +193,32 @@ int encode_tiled_on_device(
     a.num_tiles = (uint32_t)num_tiles;
     a.eos_padding = ctx->tables.eos_padding;
     if (const char *exp = getenv("AWS_HUFFMAN_BATCH_EXPERIMENT")) a.debug = (uint32_t)atoi(exp);
-    const uint64_t num_macro = (num_tiles + kEncSub - 1) / kEncSub;  // one look-back descriptor each
-    const unsigned grid = (unsigned)std::min<uint64_t>(num_macro, (uint64_t)ctx->sm_count * 4);
     if (seg) {
         HB_CUDA_TRY(sc.tile_first.reserve((num_tiles + 1) * sizeof(uint32_t)));
         a.tile_first = sc.tile_first.as<uint32_t>();
         tile_index_kernel<<<(unsigned)((num_tiles + 1 + 255) / 256), 256, 0, stream>>>(
             v.in_offsets, v.n, total_in, num_tiles, sc.tile_first.as<uint32_t>());
         ++ctx->launches;
-        HB_CUDA_TRY(cudaFuncSetAttribute(
-            encode_tiled_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEncSmemBytes));
-        encode_tiled_kernel<true><<<grid, kEncThreads, kEncSmemBytes, stream>>>(ctx->tables.enc, a);
-    } else {
-        HB_CUDA_TRY(cudaFuncSetAttribute(
-            encode_tiled_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEncSmemBytes));
-        encode_tiled_kernel<false><<<grid, kEncThreads, kEncSmemBytes, stream>>>(ctx->tables.enc, a);
     }
+    if (!ctx->enc_blocks_per_sm[seg]) {
+        int per_sm = 0;
+        if (seg) {
+            HB_CUDA_TRY(cudaFuncSetAttribute(
+                encode_tiled_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEncSmemBytes));
+            HB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                &per_sm, encode_tiled_kernel<true>, kEncBlock, kEncSmemBytes));
+        } else {
+            HB_CUDA_TRY(cudaFuncSetAttribute(
+                encode_tiled_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEncSmemBytes));
+            HB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                &per_sm, encode_tiled_kernel<false>, kEncBlock, kEncSmemBytes));
+        }
+        ctx->enc_blocks_per_sm[seg] = std::max(1, per_sm);
+    }
+    const unsigned grid =
+        (unsigned)std::min<uint64_t>(num_tiles, (uint64_t)ctx->sm_count * ctx->enc_blocks_per_sm[seg]);
+    if (seg) encode_tiled_kernel<true><<<grid, kEncBlock, kEncSmemBytes, stream>>>(ctx->tables.enc, a);
+    else encode_tiled_kernel<false><<<grid, kEncBlock, kEncSmemBytes, stream>>>(ctx->tables.enc, a);
     ++ctx->launches;
     HB_CUDA_TRY(cudaGetLastError());
     if (v.out_lens || v.status || v.consumed || v.overflow_pattern || v.overflow_num_bits) {
@@ -224,7 +235,8 @@ int encode_on_device(
     aws_huffman_batch_ctx *ctx, Scratch &sc, hb::BatchView v, uint64_t total_in, cudaStream_t stream) {
     if (v.n == 0) return AWS_OP_SUCCESS;
     const bool force_generic = getenv("AWS_HUFFMAN_BATCH_FORCE_GENERIC") != nullptr;
-    if (!v.out_caps && !ctx->tables.has_unknown && total_in > 0 && v.n < 0xffffffffull &&
+    // (the tiled kernel's multiply-add accumulator needs 1 << len to fit a word: codes of up to 31 bits)
+    if (!v.out_caps && !ctx->tables.has_unknown && ctx->tables.max_len <= 31 && total_in > 0 && v.n < 0xffffffffull &&
         (total_in + kEncTile - 1) / kEncTile < 0xffffffffull && !force_generic) {
         return encode_tiled_on_device(ctx, sc, v, total_in, stream);
     }
