@@ -277,11 +277,14 @@ __device__ __forceinline__ void enc_append(uint32_t &sp, uint32_t &acc, uint32_t
 __device__ __forceinline__ uint32_t smem_addr(const void *p) {
     return (uint32_t)__cvta_generic_to_shared(p);
 }
-// Table entry of byte `k` of `word`; `tab` is the shared-window address of the table.
+// Table entry of byte `k` of `word`. The table is replicated 16 times, entry s of copy j at
+// (16 s + j) * 8: every lane of a half-warp reads from its own pair of banks (copy lane % 16), so a
+// lookup is conflict-free whatever the symbols are. `tab` = shared-window address of MY copy's entry 0.
+constexpr int kEncTabCopies = 16;
 __device__ __forceinline__ uint2 enc_lookup(uint32_t tab, uint32_t word, int k) {
     const uint32_t byte = __byte_perm(word, 0, 0x4440 | (k & 3));
     uint32_t addr;
-    asm("mad.lo.u32 %0, %1, 8, %2;" : "=r"(addr) : "r"(byte), "r"(tab));
+    asm("mad.lo.u32 %0, %1, %3, %2;" : "=r"(addr) : "r"(byte), "r"(tab), "n"(8 * kEncTabCopies));
     uint2 e;
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(e.x), "=r"(e.y) : "r"(addr));
     return e;
@@ -364,6 +367,7 @@ __device__ __forceinline__ void enc_copy_piece(
         const uint32_t *src = st + ((d + 32 * (int)j_lo) >> 5);
         uint32_t *dst = reinterpret_cast<uint32_t *>(base) + j_lo;
         const uint32_t nwords = j_hi - j_lo;
+#pragma unroll 2
         for (uint32_t i = tid; i < nwords; i += kEncThreads)
             dst[i] = __byte_perm(__funnelshift_l(src[i + 1], src[i], sh), 0, 0x0123);
     }
@@ -381,8 +385,33 @@ __device__ __forceinline__ void enc_copy_piece(
     }
 }
 
+// The words shared by neighbouring warps and the tile's last, partial word: warp w's first completed word
+// still lacks what the warps before it left over (s_tail). Called by every worker warp after a barrier
+// that follows the packing. Normally every warp completed a word, so lane 0 of warp w simply ORs warp
+// w-1's leftover into its first word; otherwise (tiny tiles) warp 1 runs a segmented OR-scan over the warps.
+__device__ __forceinline__ void enc_fix_warp_boundaries(
+    uint32_t *stage, const uint32_t *s_tail, const uint32_t *s_brk, const uint32_t *s_wpos, uint32_t warp, uint32_t lane) {
+    const uint32_t brk = lane < kEncWarps ? s_brk[lane] : 1u;
+    const uint32_t endpos = s_wpos[kEncWarps];
+    if (__all_sync(0xffffffffu, brk)) {
+        if (lane == 0 && warp > 0) {
+            const uint32_t cin = s_tail[warp - 1];
+            if (cin) stage[s_wpos[warp] >> 5] |= cin;
+        }
+        if (lane == 1 && warp == kEncWarps - 1 && (endpos & 31u)) stage[endpos >> 5] = s_tail[kEncWarps - 1];
+    } else if (warp == 1) {
+        uint32_t v = lane < kEncWarps ? s_tail[lane] : 0u;
+        uint32_t f = lane < kEncWarps ? s_brk[lane] : 0u;
+        enc_seg_or_scan(v, f, lane);
+        uint32_t cin = __shfl_up_sync(0xffffffffu, v, 1);
+        if (lane == 0) cin = 0;
+        if (lane < kEncWarps && brk && cin) stage[s_wpos[lane] >> 5] |= cin;  // where warp `lane` starts in the stage
+        if (lane == kEncWarps - 1 && (endpos & 31u)) stage[endpos >> 5] = v;
+    }
+}
+
 constexpr size_t kEncSmemBytes =
-    kEncStageWords * 4 + kEncTile * 2 /* item start positions */ + 2048 /* code table */ + kEncTile /* symbols */;
+    kEncStageWords * 4 + kEncTile * 2 /* item start positions */ + 2048 * kEncTabCopies /* code table */ + kEncTile /* symbols */;
 
 // Persistent blocks of 8 WORKER warps + 1 SCOUT warp; tiles come from an atomic ticket.
 //
@@ -391,10 +420,10 @@ constexpr size_t kEncSmemBytes =
 // The workers therefore never wait for a look-back before they publish: per tile t they run
 //
 //     measure(t)  lookups, scan, publish the tile's function          (worker barrier A)
-//     X(t)        rendezvous with the scout: hand it tile t, receive G(t-1)
+//     hand tile t to the scout (arrive, no wait); wait for G(t-1) (normally there since long)
 //     ticket(t+1) + copy-out(t-1)                                      (worker barrier B)
 //     fetch(t+1)  symbols, item range (loads in flight during the packing)
-//     pack(t)     into the stage                                       (worker barrier C)
+//     pack(t)     into the stage                                       (batches: worker barrier C)
 //
 // and the scout resolves G(t) — the decoupled look-back, a chain of dependent L2 round trips — while
 // the workers copy out t-1, pack t and measure t+1: a whole tile of slack. It also computes the bits
@@ -402,8 +431,12 @@ constexpr size_t kEncSmemBytes =
 constexpr int kEncBlock = kEncThreads + 32;
 constexpr uint32_t kEncDone = 0xffffffffu;
 
-__device__ __forceinline__ void enc_worker_sync() { asm volatile("bar.sync 2, %0;" ::"n"(kEncThreads) : "memory"); }
-__device__ __forceinline__ void enc_rendezvous() { asm volatile("bar.sync 1, %0;" ::"n"(kEncBlock) : "memory"); }
+// Named barriers. Workers among themselves: 1. Hand-off of a tile to the scout: 2 + parity (workers
+// arrive without waiting, the scout waits). Result of a look-back: 4 + parity (the scout arrives, the
+// workers wait — normally not at all, the result has been there for most of a tile).
+__device__ __forceinline__ void enc_worker_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEncThreads) : "memory"); }
+__device__ __forceinline__ void enc_bar_arrive(uint32_t id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(kEncBlock) : "memory"); }
+__device__ __forceinline__ void enc_bar_sync(uint32_t id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kEncBlock) : "memory"); }
 
 struct EncHandoff {   // worker thread 0 -> scout, double buffered by iteration parity
     uint32_t tile;    // kEncDone: no more tiles
@@ -419,24 +452,29 @@ template <bool kSeg>
 __global__ void __launch_bounds__(kEncBlock, kEncSymsPerThread == 32 ? 2 : 3) encode_tiled_kernel(const uint2 *__restrict__ enc_table, EncTiledArgs a) {
     __shared__ uint32_t s_mask[kEncTile / 32];
     __shared__ Seg s_wseg[kEncWarps];
-    __shared__ uint32_t s_tail[kEncWarps], s_brk[kEncWarps];
+    __shared__ uint32_t s_tail[kEncWarps], s_brk[kEncWarps], s_wpos[kEncWarps + 1];
     __shared__ uint32_t s_next;
     __shared__ EncHandoff s_hand[2];
     __shared__ EncResult s_res[2];
     extern __shared__ __align__(16) uint8_t s_dyn[];
     uint32_t *const stage = reinterpret_cast<uint32_t *>(s_dyn);
     uint16_t *const obpos = reinterpret_cast<uint16_t *>(s_dyn + kEncStageWords * 4);
-    const uint32_t tab = smem_addr(s_dyn + kEncStageWords * 4 + kEncTile * 2);
+    const uint32_t tab0 = smem_addr(s_dyn + kEncStageWords * 4 + kEncTile * 2);
     const uint32_t stage_addr = smem_addr(stage);
-    const uint32_t sym_addr = tab + 2048;
+    const uint32_t sym_addr = tab0 + 2048 * kEncTabCopies;
 
     const uint32_t tid = threadIdx.x;
     const uint32_t lane = tid & 31, warp = tid >> 5;
+    const uint32_t tab = tab0 + (lane & (kEncTabCopies - 1)) * 8;  // my copy of the table
 
     if (tid == 0) s_next = atomicAdd(a.ticket, 1u);
     if (tid < 256) {
         const uint2 e = enc_table[tid];
-        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(tab + tid * 8), "r"(e.x), "r"(enc_len_fields(e.y)) : "memory");
+#pragma unroll
+        for (int j = 0; j < kEncTabCopies; ++j)
+            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(tab0 + (tid * kEncTabCopies + j) * 8), "r"(e.x),
+                         "r"(enc_len_fields(e.y))
+                         : "memory");
     }
     if (kSeg && tid < kEncTile / 32) s_mask[tid] = 0;
     __syncthreads();
@@ -444,7 +482,7 @@ __global__ void __launch_bounds__(kEncBlock, kEncSymsPerThread == 32 ? 2 : 3) en
     // ================================ scout =========================================================================
     if (warp == kEncWarps) {
         for (uint32_t it = 0;; ++it) {
-            enc_rendezvous();  // X
+            enc_bar_sync(2 + (it & 1));  // the workers handed over a tile
             const uint32_t tile = s_hand[it & 1].tile;
             if (tile == kEncDone) return;
             const Seg total = s_hand[it & 1].total;
@@ -488,6 +526,7 @@ __global__ void __launch_bounds__(kEncBlock, kEncSymsPerThread == 32 ? 2 : 3) en
                 s_res[it & 1].G = G0;
                 s_res[it & 1].fill = bits;
             }
+            enc_bar_arrive(4 + (it & 1));  // result ready
         }
     }
 
@@ -609,10 +648,14 @@ __global__ void __launch_bounds__(kEncBlock, kEncSymsPerThread == 32 ? 2 : 3) en
                 s_hand[it & 1].total = total;
             }
             if (kSeg && tid < kEncTile / 32) s_mask[tid] = 0;  // everybody has read its bits of this tile
-        } else if (tid == 0) {
-            s_hand[it & 1].tile = kEncDone;
+        } else {
+            if (tid == 0) s_hand[it & 1].tile = kEncDone;
+            if (prev_valid) enc_worker_sync();  // the previous tile is completely packed
         }
-        enc_rendezvous();  // X: the scout takes tile `tile`; G of the previous tile is in s_res[(it - 1) & 1]
+        // (barrier A, or the one just above, separates this from the packing of the previous tile)
+        if (prev_valid) enc_fix_warp_boundaries(stage, s_tail, s_brk, s_wpos, warp, lane);
+        enc_bar_arrive(2 + (it & 1));                       // the scout may take tile `tile`
+        if (prev_valid) enc_bar_sync(4 + ((it - 1) & 1));  // G of the previous tile is in s_res[(it - 1) & 1]
         if (cur_valid && tid == 0) s_next = atomicAdd(a.ticket, 1u);  // nothing this block waits for lies ahead
 
         // ---- copy out the previous tile ------------------------------------------------------------------------
@@ -715,33 +758,23 @@ __global__ void __launch_bounds__(kEncBlock, kEncSymsPerThread == 32 ? 2 : 3) en
                 s_tail[warp] = v;
                 s_brk[warp] = any != 0;
             }
+            if (lane == 0) s_wpos[warp] = pos0;
+            if (tid == 0) s_wpos[kEncWarps] = total.hb ? Q + total.tail : total.head;
         }
-        if (kSeg && next < a.num_tiles) {
-            // item starts of the next tile -> one bit per symbol
-            const uint64_t nt0 = (uint64_t)next * kEncTile;
-            if (ntf0 + tid < ntf1) {
-                const uint32_t p = (uint32_t)(next_item_off - nt0);
-                atomicOr(&s_mask[p >> 5], 1u << (p & 31));
+        if (kSeg) {
+            if (next < a.num_tiles) {
+                // item starts of the next tile -> one bit per symbol
+                const uint64_t nt0 = (uint64_t)next * kEncTile;
+                if (ntf0 + tid < ntf1) {
+                    const uint32_t p = (uint32_t)(next_item_off - nt0);
+                    atomicOr(&s_mask[p >> 5], 1u << (p & 31));
+                }
+                for (uint32_t i = ntf0 + tid + kEncThreads; i < ntf1; i += kEncThreads) {
+                    const uint32_t p = (uint32_t)(a.in_offsets[i] - nt0);
+                    atomicOr(&s_mask[p >> 5], 1u << (p & 31));
+                }
             }
-            for (uint32_t i = ntf0 + tid + kEncThreads; i < ntf1; i += kEncThreads) {
-                const uint32_t p = (uint32_t)(a.in_offsets[i] - nt0);
-                atomicOr(&s_mask[p >> 5], 1u << (p & 31));
-            }
-        }
-        enc_worker_sync();  // C
-
-        // ---- 4. words shared by neighbouring warps, the tile's last partial word ---------------------------------
-        if (warp == 1) {
-            uint32_t v = lane < kEncWarps ? s_tail[lane] : 0u;
-            uint32_t f = lane < kEncWarps ? s_brk[lane] : 0u;
-            const uint32_t brk = f;
-            enc_seg_or_scan(v, f, lane);
-            uint32_t cin = __shfl_up_sync(0xffffffffu, v, 1);
-            if (lane == 0) cin = 0;
-            const uint32_t wpos = we.hb ? Q + we.tail : we.head;  // where warp `lane` starts in the stage
-            if (lane < kEncWarps && brk && cin) stage[wpos >> 5] |= cin;
-            const uint32_t endpos = total.hb ? Q + total.tail : total.head;
-            if (lane == kEncWarps - 1 && (endpos & 31u)) stage[endpos >> 5] = v;
+            enc_worker_sync();  // C: the mask of the next tile is complete
         }
 
         prev_valid = true;
