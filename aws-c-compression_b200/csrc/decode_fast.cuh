@@ -279,6 +279,17 @@ struct WordWriter {
     }
 };
 
+// Emits symbols as single bytes into shared memory (a row that belongs to the emitting thread alone).
+// A two-symbol entry is two byte stores; nothing else is tracked (the count is the address difference).
+struct ByteEmitter {
+    uint32_t addr;  // shared-window byte address of the next symbol
+    template <bool kSecond>
+    __device__ __forceinline__ void put(uint32_t entry) {
+        asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(entry >> (kSecond ? 16 : 8)) : "memory");
+        ++addr;
+    }
+};
+
 struct SpanS {
     uint32_t pos;   // stage-relative bit position after the last decoded symbol
     uint32_t nsym;
@@ -287,10 +298,10 @@ struct SpanS {
 
 // Decodes from stage bit `pos` until `stop`; the stream itself ends at `end` (stop <= end; both are
 // stage-relative bit positions). Same rules as decode_span.
-template <bool kWrite, bool kPadded, bool kSkipHoles>
+template <bool kWrite, bool kPadded, bool kSkipHoles, typename Writer = WordWriter>
 __device__ __forceinline__ SpanS decode_smem(
     const uint32_t *s_in, const uint32_t *s_lut, uint32_t root_bits, uint32_t pos, uint32_t stop, uint32_t end,
-    WordWriter *writer) {
+    Writer *writer) {
     SpanS r;
     uint32_t nsym = 0;
     uint32_t term = kTermStop;
@@ -389,50 +400,207 @@ __device__ __forceinline__ SpanS decode_smem(
 }
 
 // ---------------------------------------------------------------------------------------------
+// The hot loop of the single-pass decoders: two symbols per lookup straight from the staged stream,
+// symbols emitted as bytes into the thread's shared-memory row. Hand-tightened (shared-window
+// addresses, PTX loads/stores) because this loop is most of the decode time:
+//   * a lane that meets a code longer than the root index PARKS by setting its position to ~0 (so the
+//     one loop test "pos < pair_end" also skips parked lanes); parked lanes are resolved together
+//     after kSteps steps
+//   * both symbol bytes of an entry are always stored and the address advances by the entry's count:
+//     no branch; a one-symbol entry leaves a stray byte that the next store overwrites (rows have room
+//     for one byte more than they can hold)
+// Runs while at least 32 + root_bits real bits follow `pos`; the caller finishes the span with
+// decode_smem (one symbol per lookup, end-of-stream rules).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+// Returns kTermStop, or kTermUnknown when a window with >= 32 real bits matched no code (!kSkipHoles).
+template <bool kEmit, bool kPadded, bool kSkipHoles>
+__device__ __forceinline__ uint32_t decode_pairs(
+    const uint32_t *s_in, const uint32_t *s_lut, uint32_t root_bits, uint32_t &pos, uint32_t pair_end, uint32_t &out_addr) {
+    constexpr int kSteps = 6;
+    constexpr uint32_t kParked = 0x80000000u;  // positions are far below 2^31: a parked lane fails "pos < pair_end"
+    if (pos >= pair_end) return kTermStop;
+    uint32_t in_addr = (uint32_t)__cvta_generic_to_shared(s_in);
+    uint32_t lut_addr = (uint32_t)__cvta_generic_to_shared(s_lut);
+    // (opaque copy: otherwise the compiler re-derives the base from the shared window in every step)
+    asm volatile("mov.u32 %0, %0;" : "+r"(lut_addr));
+    const uint32_t shift = 32 - root_bits;
+    // The stream words under the cursor live in registers: w0 holds bit `pos`, w1 the word after it, w2 is
+    // fetched one word ahead, so the dependent chain of a step is funnel -> LUT load -> add and the stream
+    // loads are off it. A span never leaves its padded row in here (the callers' spans end at a row
+    // boundary and pair_end lies 12+ bits before it), so the words are consecutive in shared memory.
+    uint32_t wa = in_addr + (kPadded ? (pos >> 5) + (pos >> 10) : (pos >> 5)) * 4;
+    uint32_t w0 = lds_u32(wa), w1 = lds_u32(wa + 4), w2 = lds_u32(wa + 8);
+    wa += 12;
+    int limit = (int)((pos | 31u) + 1u);  // first bit after w0
+    while (pos < pair_end) {
+#pragma unroll
+        for (int step = 0; step < kSteps; ++step) {
+            if (pos < pair_end) {
+                const uint32_t e = lds_u32(lut_addr + ((__funnelshift_l(w1, w0, pos) >> shift) << 2));
+                if (dlut_is_leaf(e)) {
+                    pos += e >> 24;
+                    if (kEmit) {
+                        sts_u8(out_addr, e >> 8);
+                        sts_u8(out_addr + 1, e >> 16);
+                        out_addr += e & 3u;
+                    }
+                } else {
+                    pos |= kParked;
+                }
+                if ((int)pos >= limit) {  // (a parked position is negative)
+                    w0 = w1;
+                    w1 = w2;
+                    w2 = lds_u32(wa);
+                    wa += 4;
+                    limit += 32;
+                }
+            }
+        }
+        if (pos & kParked) {
+            pos &= ~kParked;
+            const uint32_t window = __funnelshift_l(w1, w0, pos);
+            const uint32_t e = dec_walk(s_lut, root_bits, window, s_lut[window >> shift]);
+            if (e == 0) {
+                if (!kSkipHoles) return kTermUnknown;
+                ++pos;
+            } else {
+                pos += dlut_len1(e);
+                if (kEmit) {
+                    sts_u8(out_addr, e >> 8);
+                    ++out_addr;
+                }
+            }
+            if ((int)pos >= limit) {
+                w0 = w1;
+                w1 = w2;
+                w2 = lds_u32(wa);
+                wa += 4;
+                limit += 32;
+            }
+        }
+    }
+    return kTermStop;
+}
+
+// A span decoded by decode_pairs + decode_smem's careful tail. nsym is only meaningful when emitting.
+template <bool kEmit, bool kPadded, bool kSkipHoles>
+__device__ __forceinline__ SpanS decode_span_smem(
+    const uint32_t *s_in, const uint32_t *s_lut, uint32_t root_bits, uint32_t pos, uint32_t stop, uint32_t end,
+    uint32_t out_addr) {
+    const uint32_t fast_end = (end >= 32u) ? min(stop, end - 31u) : 0u;
+    const uint32_t pair_end = fast_end > root_bits ? fast_end - root_bits : 0u;
+    const uint32_t out0 = out_addr;
+    if (decode_pairs<kEmit, kPadded, kSkipHoles>(s_in, s_lut, root_bits, pos, pair_end, out_addr) == kTermUnknown) {
+        SpanS r;
+        r.pos = pos;
+        r.nsym = out_addr - out0;
+        r.term = kTermUnknown;
+        return r;
+    }
+    ByteEmitter em;
+    em.addr = out_addr;
+    SpanS r = decode_smem<kEmit, kPadded, kSkipHoles>(s_in, s_lut, root_bits, pos, stop, end, &em);
+    r.nsym = em.addr - out0;
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Batch of independent strings
 // ---------------------------------------------------------------------------------------------
 constexpr int kDecThreads = 256;
 constexpr int kDecWarps = kDecThreads / 32;
-constexpr int kDecItemsPerTile = 384;           // strings per tile (12 groups of 32)
-constexpr uint32_t kDecStageWords = 11 * 1024;  // 44 KiB of encoded bytes per tile
+constexpr int kDecItemsPerTile = 288;        // strings per tile (9 groups of 32)
+constexpr uint32_t kDecMaxRow = 4096;        // a staged string decodes to at most this many bytes
+constexpr uint32_t kDecRowSlack = 8;         // spare bytes per row (alignment, the emitter's look-ahead byte)
 
 struct DecBatchArgs {
     BatchView b;
     const uint32_t *lut;
     uint32_t lut_count;
     uint32_t root_bits;
+    uint32_t min_len;      // shortest code: a string of L bytes decodes to at most 8 L / min_len symbols
+    uint32_t stage_words;  // capacity of the input stage
+    uint32_t rows_bytes;   // capacity of the row area
     uint64_t *tile_state;
     uint32_t *ticket;
     uint32_t num_tiles;
 };
 
-// One thread per string, but strings are first SORTED BY LENGTH inside the tile (counting sort in
-// shared memory) and handed to warps in groups of 32 similar lengths, longest first: a warp's lanes
-// then leave the decode loop almost together instead of waiting for the longest string of a random
-// group, and warps pull groups dynamically so the block stays busy.
-// Dynamic shared memory: [LUT][stage words + 2 zero words]
-__global__ void __launch_bounds__(kDecThreads) decode_batch_kernel(DecBatchArgs a) {
-    extern __shared__ uint32_t s_lut[];  // [LUT][stage]
-    uint32_t *s_in = s_lut + a.lut_count;
+// Thread-serial copy of n bytes inside shared memory; src is 4-byte aligned, dst is not.
+__device__ __forceinline__ void smem_copy_row(const uint8_t *src, uint8_t *dst, uint32_t n) {
+    if (n == 0) return;
+    const uint32_t head = min(n, (4u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 3)) & 3u);
+    for (uint32_t i = 0; i < head; ++i) dst[i] = src[i];
+    const uint32_t body = (n - head) >> 2;  // whole destination words
+    if (body) {
+        const uint32_t *sw = reinterpret_cast<const uint32_t *>(src);
+        uint32_t *dw = reinterpret_cast<uint32_t *>(dst + head);
+        const uint32_t sel = 0x3210u + 0x1111u * head;  // bytes head .. head + 3 of a word pair
+        uint32_t lo = sw[0];
+        for (uint32_t j = 0; j < body; ++j) {
+            const uint32_t hi = sw[j + 1];
+            dw[j] = __byte_perm(lo, hi, sel);
+            lo = hi;
+        }
+    }
+    for (uint32_t i = head + 4 * body; i < n; ++i) dst[i] = src[i];
+}
+
+// One thread per string, single pass. Persistent 256-thread blocks, the whole decode LUT in shared
+// memory. Per tile of kDecItemsPerTile strings:
+//   1. the encoded bytes are staged as big-endian words (coalesced 128-bit loads); strings are SORTED
+//      BY LENGTH (counting sort in shared memory) and handed to warps in groups of 32 similar lengths,
+//      longest first, warps pulling groups dynamically, so lanes leave the decode loop together
+//   2. every string is decoded ONCE; its symbols go byte by byte into a private row of shared memory
+//      (row i starts where the string could start at worst: 8 * offset / min_len)
+//   3. a block scan of the symbol counts + a single-pass decoupled look-back give every string its
+//      output offset
+//   4. every thread moves its rows to their final place in a DENSE shared-memory image of the tile's
+//      output (laid out with the alignment of its global address), which is then copied out with
+//      128-bit coalesced stores. The dense image reuses the input stage and the front of the row area:
+//      rows that start in that front part are moved first (their destination lies inside the stage),
+//      the others after a barrier (their destination may overlap rows that are already gone).
+// A tile whose strings do not fit the stage is decoded straight from global memory in two passes.
+// Dynamic shared memory: [LUT][stage words + 2][rows]
+__global__ void __launch_bounds__(kDecThreads, 2) decode_batch_kernel(DecBatchArgs a) {
+    extern __shared__ __align__(16) uint32_t s_lut[];  // [LUT][stage][rows]
+    const uint32_t lut_pad = (a.lut_count + 3u) & ~3u;
+    uint32_t *s_in = s_lut + lut_pad;
+    uint8_t *const s_dense = reinterpret_cast<uint8_t *>(s_in);  // the dense image starts where the stage does
+    const uint32_t stage_bytes = (a.stage_words + 2) * 4;         // (+2 zero words for the window look-ahead)
+    uint8_t *const s_rows = s_dense + ((stage_bytes + 15u) & ~15u);
     __shared__ uint32_t s_start[kDecItemsPerTile];  // first bit of the string in the stage
     __shared__ uint32_t s_bytes[kDecItemsPerTile];  // encoded length
-    __shared__ uint32_t s_cnt[kDecItemsPerTile];    // symbols per string, then exclusive offsets within the tile
+    __shared__ uint32_t s_cnt[kDecItemsPerTile];    // symbols per string
+    __shared__ uint32_t s_off[kDecItemsPerTile];    // exclusive offsets within the tile
+    __shared__ uint32_t s_row[kDecItemsPerTile];    // start of the string's row in the row area
     __shared__ uint16_t s_perm[kDecItemsPerTile];   // strings in order of decreasing length
     static_assert(kDecItemsPerTile <= 2 * kDecThreads, "the block scan handles two strings per thread");
     __shared__ uint32_t s_hist[256];
     __shared__ uint64_t s_warp_sum[kDecWarps];
     __shared__ uint64_t s_prefix;
-    __shared__ uint32_t s_tile, s_next;
+    __shared__ uint32_t s_tile, s_next, s_fits;
 
     for (uint32_t i = threadIdx.x; i < a.lut_count; i += kDecThreads) s_lut[i] = a.lut[i];
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
     const BatchView &b = a.b;
+    const uint32_t rows_addr = (uint32_t)__cvta_generic_to_shared(s_rows);
 
     while (true) {
         __syncthreads();  // previous tile fully done (and the LUT is in place on the first trip)
         if (threadIdx.x == 0) {
             s_tile = atomicAdd(a.ticket, 1u);
             s_next = kDecWarps;
+            s_fits = 1;
         }
         for (uint32_t i = threadIdx.x; i < 256; i += kDecThreads) s_hist[i] = 0;
         __syncthreads();
@@ -442,37 +610,44 @@ __global__ void __launch_bounds__(kDecThreads) decode_batch_kernel(DecBatchArgs 
         const uint32_t nitems = (uint32_t)min((uint64_t)kDecItemsPerTile, b.n - item0);
         const uint32_t ngroups = (nitems + 31) / 32;
 
-        // ---- stage the tile's encoded bytes as big-endian words; histogram of string lengths -----------------
+        // ---- string table: where each string starts in the stage and in the row area; length histogram -------
         const uint64_t byte0 = b.in_offsets[item0], byte1 = b.in_offsets[item0 + nitems];
         const uintptr_t addr0 = reinterpret_cast<uintptr_t>(b.in) + byte0;
         const uint32_t lead = (uint32_t)(addr0 & 15);  // the stage starts on a 16-byte boundary
         const uint64_t nwords64 = (byte1 - byte0 + lead + 3) >> 2;
-        const bool staged = nwords64 <= kDecStageWords;
+        // row i starts at 4 * ceil(2 * offset / min_len) + slack * i: never before the end of row i - 1
+        const uint64_t rows_need = 4 * ((2 * (byte1 - byte0) + a.min_len - 1) / a.min_len) + (uint64_t)kDecRowSlack * (nitems + 1);
+        bool fits = nwords64 <= a.stage_words && rows_need <= a.rows_bytes;
+        for (uint32_t it = threadIdx.x; it < nitems; it += kDecThreads) {
+            const uint64_t in0 = b.in_offsets[item0 + it];
+            const uint64_t len = b.in_offsets[item0 + it + 1] - in0;
+            s_start[it] = (uint32_t)(in0 - byte0) * 8 + lead * 8;
+            s_bytes[it] = (uint32_t)min(len, (uint64_t)0xffffffffu);
+            s_row[it] = 4 * (uint32_t)((2 * (in0 - byte0) + a.min_len - 1) / a.min_len) + kDecRowSlack * it;
+            if (8 * len / a.min_len + kDecRowSlack > kDecMaxRow) s_fits = 0;
+            atomicAdd(&s_hist[255 - (uint32_t)min(len, (uint64_t)255)], 1u);
+        }
+        __syncthreads();
+        const bool staged = fits && s_fits != 0;
         if (staged) {
+            // ---- stage the tile's encoded bytes as big-endian words -------------------------------------------
             const uint32_t nwords = (uint32_t)nwords64;
             const uint32_t nquads = nwords >> 2;  // whole 128-bit loads; the ragged end goes word by word
             const uint4 *g4 = reinterpret_cast<const uint4 *>(addr0 - lead);
             for (uint32_t j = threadIdx.x; j < nquads; j += kDecThreads) {
                 const uint4 v = __ldg(g4 + j);
-                uint32_t *dst = s_in + 4 * j;
-                dst[0] = __byte_perm(v.x, 0, 0x0123);
-                dst[1] = __byte_perm(v.y, 0, 0x0123);
-                dst[2] = __byte_perm(v.z, 0, 0x0123);
-                dst[3] = __byte_perm(v.w, 0, 0x0123);
+                uint4 o;
+                o.x = __byte_perm(v.x, 0, 0x0123);
+                o.y = __byte_perm(v.y, 0, 0x0123);
+                o.z = __byte_perm(v.z, 0, 0x0123);
+                o.w = __byte_perm(v.w, 0, 0x0123);
+                reinterpret_cast<uint4 *>(s_in)[j] = o;
             }
             const uint32_t *gw = reinterpret_cast<const uint32_t *>(addr0 - lead);
             for (uint32_t j = 4 * nquads + threadIdx.x; j < nwords; j += kDecThreads)
                 s_in[j] = __byte_perm(__ldg(gw + j), 0, 0x0123);
             if (threadIdx.x < 2) s_in[nwords + threadIdx.x] = 0;
         }
-        for (uint32_t it = threadIdx.x; it < nitems; it += kDecThreads) {
-            const uint64_t in0 = b.in_offsets[item0 + it];
-            const uint64_t len = b.in_offsets[item0 + it + 1] - in0;
-            s_start[it] = (uint32_t)(in0 - byte0) * 8 + lead * 8;
-            s_bytes[it] = (uint32_t)min(len, (uint64_t)0xffffffffu);
-            atomicAdd(&s_hist[255 - (uint32_t)min(len, (uint64_t)255)], 1u);
-        }
-        __syncthreads();
         if (warp == 0) {
             // exclusive scan of the 256 bins, 8 per lane
             uint32_t v[8], sum = 0;
@@ -495,7 +670,7 @@ __global__ void __launch_bounds__(kDecThreads) decode_batch_kernel(DecBatchArgs 
         }
         __syncthreads();
 
-        // ---- count ---------------------------------------------------------------------------------------------
+        // ---- decode (staged: once, into the rows; otherwise: count) ------------------------------------------
         for (uint32_t g = warp; g < ngroups;) {
             const uint32_t slot = g * 32 + lane;
             if (slot < nitems) {
@@ -506,7 +681,7 @@ __global__ void __launch_bounds__(kDecThreads) decode_batch_kernel(DecBatchArgs 
                 uint32_t nsym, term;
                 if (staged) {
                     const uint32_t ib = s_start[it], ie = ib + nbytes * 8;
-                    const SpanS r = decode_smem<false, false, false>(s_in, s_lut, a.root_bits, ib, ie, ie, nullptr);
+                    const SpanS r = decode_span_smem<true, false, false>(s_in, s_lut, a.root_bits, ib, ie, ie, rows_addr + s_row[it]);
                     cbits = r.pos - ib;
                     nsym = r.nsym;
                     term = r.term;
@@ -551,40 +726,60 @@ __global__ void __launch_bounds__(kDecThreads) decode_batch_kernel(DecBatchArgs 
             if (lane == 0) s_prefix = prefix;
         }
         __syncthreads();
+        const uint64_t tile_base = s_prefix;
         {
-            const uint64_t tile_base = s_prefix;
             const uint64_t e0 = s_warp_sum[warp] + (incl - mine);  // exclusive, within the tile
             if (2 * threadIdx.x < nitems) {
-                s_cnt[2 * threadIdx.x] = (uint32_t)e0;
+                s_off[2 * threadIdx.x] = (uint32_t)e0;
                 b.out_offsets[item0 + 2 * threadIdx.x] = tile_base + e0;
                 if (b.out_lens) b.out_lens[item0 + 2 * threadIdx.x] = c0;
                 if (item0 + 2 * threadIdx.x + 1 == b.n) b.out_offsets[b.n] = tile_base + e0 + c0;
             }
             if (2 * threadIdx.x + 1 < nitems) {
-                s_cnt[2 * threadIdx.x + 1] = (uint32_t)(e0 + c0);
+                s_off[2 * threadIdx.x + 1] = (uint32_t)(e0 + c0);
                 b.out_offsets[item0 + 2 * threadIdx.x + 1] = tile_base + e0 + c0;
                 if (b.out_lens) b.out_lens[item0 + 2 * threadIdx.x + 1] = c1;
                 if (item0 + 2 * threadIdx.x + 2 == b.n) b.out_offsets[b.n] = tile_base + e0 + c0 + c1;
             }
             if (threadIdx.x == 0) s_next = kDecWarps;
+            if (threadIdx.x == kDecThreads - 1) s_hist[0] = (uint32_t)(e0 + c0 + c1);  // symbols in the tile
         }
         __syncthreads();
 
-        // ---- write: decode again, now storing -------------------------------------------------------------------
-        const uint64_t tile_base = s_prefix;
-        for (uint32_t g = warp; g < ngroups;) {
-            const uint32_t slot = g * 32 + lane;
-            if (slot < nitems) {
-                const uint32_t it = s_perm[slot];
-                const uint64_t off = tile_base + s_cnt[it];
-                const uint64_t room = off < b.out_capacity ? b.out_capacity - off : 0;
-                if (staged) {
-                    WordWriter wr;
-                    wr.init(b.out + off, room);
-                    const uint32_t ib = s_start[it], ie = ib + s_bytes[it] * 8;
-                    decode_smem<true, false, false>(s_in, s_lut, a.root_bits, ib, ie, ie, &wr);
-                    wr.finish();
-                } else {
+        if (staged) {
+            // ---- rows -> dense image (aligned like the global destination) -> global -----------------------------
+            const uint32_t total = s_hist[0];
+            const uint32_t pad = (uint32_t)((reinterpret_cast<uintptr_t>(b.out) + tile_base) & 15);
+            // rows that start before `front` lie where the dense image may grow: they go first (their destination
+            // ends inside the stage area); the host sizes the areas so that the image ends before row offset `front`
+            const uint32_t front = stage_bytes > kDecMaxRow + 32 ? ((stage_bytes - kDecMaxRow - 32) & ~3u) : 0u;
+#pragma unroll 1
+            for (int phase = 0; phase < 2; ++phase) {
+                for (uint32_t it = threadIdx.x; it < nitems; it += kDecThreads) {
+                    const uint32_t row = s_row[it];
+                    if ((row < front) == (phase == 0)) smem_copy_row(s_rows + row, s_dense + pad + s_off[it], s_cnt[it]);
+                }
+                __syncthreads();
+            }
+            const uint64_t room = tile_base < b.out_capacity ? b.out_capacity - tile_base : 0;
+            const uint32_t ncopy = (uint32_t)min((uint64_t)total, room);
+            uint8_t *const g0 = b.out + tile_base;
+            const uint32_t head = min(ncopy, (16u - pad) & 15u);
+            const uint32_t nvec = (ncopy - head) >> 4;
+            const uint4 *sv = reinterpret_cast<const uint4 *>(s_dense + pad + head);
+            uint4 *gv = reinterpret_cast<uint4 *>(g0 + head);
+            for (uint32_t v = threadIdx.x; v < nvec; v += kDecThreads) gv[v] = sv[v];
+            if (threadIdx.x < head) g0[threadIdx.x] = s_dense[pad + threadIdx.x];
+            const uint32_t tail0 = head + 16 * nvec;
+            if (threadIdx.x >= 32 && threadIdx.x - 32 < ncopy - tail0) g0[tail0 + threadIdx.x - 32] = s_dense[pad + tail0 + threadIdx.x - 32];
+        } else {
+            // ---- write: decode again from global memory, now storing --------------------------------------------------
+            for (uint32_t g = warp; g < ngroups;) {
+                const uint32_t slot = g * 32 + lane;
+                if (slot < nitems) {
+                    const uint32_t it = s_perm[slot];
+                    const uint64_t off = tile_base + s_off[it];
+                    const uint64_t room = off < b.out_capacity ? b.out_capacity - off : 0;
                     const uint64_t in0 = b.in_offsets[item0 + it];
                     const uint64_t len = b.in_offsets[item0 + it + 1] - in0;
                     ByteWriter wr;
@@ -592,10 +787,10 @@ __global__ void __launch_bounds__(kDecThreads) decode_batch_kernel(DecBatchArgs 
                     decode_span<true, false>(s_lut, a.root_bits, b.in + in0, 0, len * 8, len, &wr);
                     wr.finish();
                 }
+                uint32_t next = 0;
+                if (lane == 0) next = atomicAdd(&s_next, 1u);
+                g = __shfl_sync(0xffffffffu, next, 0);
             }
-            uint32_t next = 0;
-            if (lane == 0) next = atomicAdd(&s_next, 1u);
-            g = __shfl_sync(0xffffffffu, next, 0);
         }
     }
 }
@@ -638,7 +833,9 @@ struct StreamArgs {
     const uint32_t *lut;
     uint32_t lut_count;
     uint32_t root_bits;
+    const uint32_t *gate;       // when set: these kernels only run if *gate != 0 (fallback of the fused kernel)
 };
+__device__ __forceinline__ bool stream_gate_closed(const StreamArgs &a) { return a.gate != nullptr && *a.gate == 0; }
 
 // (re)decodes one chunk from global memory; used by the rare fix-up paths
 __device__ __forceinline__ uint64_t decode_chunk_record(
@@ -690,6 +887,7 @@ __device__ __forceinline__ void stream_stage(const StreamArgs &a, uint64_t c0, u
 
 // Speculative pass: find an entry point by pre-rolling, then decode the chunk once.
 __global__ void __launch_bounds__(kStreamThreads) stream_sync_kernel(StreamArgs a) {
+    if (stream_gate_closed(a)) return;
     extern __shared__ uint32_t s_lut[];  // [LUT][stage]
     uint32_t *s_in = s_lut + a.lut_count;
     for (uint32_t i = threadIdx.x; i < a.lut_count; i += kStreamThreads) s_lut[i] = a.lut[i];
@@ -712,10 +910,10 @@ __global__ void __launch_bounds__(kStreamThreads) stream_sync_kernel(StreamArgs 
         } else {
             const uint64_t from = max(begin - kPrerollBits, a.begin_bit);
             const SpanS pre =
-                decode_smem<false, true, true>(s_in, s_lut, a.root_bits, (uint32_t)(from - origin), s_begin, s_end, nullptr);
+                decode_smem<false, true, true>(s_in, s_lut, a.root_bits, (uint32_t)(from - origin), s_begin, s_end, static_cast<WordWriter *>(nullptr));
             entry = pre.pos >= s_begin ? pre.pos - s_begin : 0u;
         }
-        const SpanS r = decode_smem<false, true, false>(s_in, s_lut, a.root_bits, s_begin + entry, s_stop, s_end, nullptr);
+        const SpanS r = decode_smem<false, true, false>(s_in, s_lut, a.root_bits, s_begin + entry, s_stop, s_end, static_cast<WordWriter *>(nullptr));
         const uint32_t exit = r.term == kTermStop ? r.pos - s_stop : 0u;
         a.chunks[k] = chunk_pack(entry, exit, r.nsym, r.term);
     }
@@ -724,6 +922,7 @@ __global__ void __launch_bounds__(kStreamThreads) stream_sync_kernel(StreamArgs 
 // One relaxation round: a chunk whose entry differs from its predecessor's exit is re-decoded from
 // there. Records are single words, so updating in place is safe; the fixed point is the true chain.
 __global__ void __launch_bounds__(kStreamThreads) stream_fix_kernel(StreamArgs a) {
+    if (stream_gate_closed(a)) return;
     extern __shared__ uint32_t s_lut[];
     for (uint32_t i = threadIdx.x; i < a.lut_count; i += kStreamThreads) s_lut[i] = a.lut[i];
     __syncthreads();
@@ -740,6 +939,7 @@ __global__ void __launch_bounds__(kStreamThreads) stream_fix_kernel(StreamArgs a
 
 // Finds the first chunk that still disagrees with its predecessor and the first terminated chunk.
 __global__ void __launch_bounds__(256) stream_verify_kernel(StreamArgs a) {
+    if (stream_gate_closed(a)) return;
     uint64_t bad = ~0ull, term = ~0ull;
     for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < a.num_chunks;
          k += (uint64_t)gridDim.x * blockDim.x) {
@@ -766,6 +966,7 @@ __global__ void __launch_bounds__(256) stream_verify_kernel(StreamArgs a) {
 // Last resort for inputs that do not self-synchronise within a few rounds: one thread walks the chain
 // from the first inconsistent chunk. Does nothing when the verify pass found no inconsistency.
 __global__ void __launch_bounds__(32) stream_repair_kernel(StreamArgs a) {
+    if (stream_gate_closed(a)) return;
     extern __shared__ uint32_t s_lut[];
     if (a.control[0] == ~0ull) return;
     for (uint32_t i = threadIdx.x; i < a.lut_count; i += 32) s_lut[i] = a.lut[i];
@@ -792,6 +993,7 @@ __global__ void __launch_bounds__(32) stream_repair_kernel(StreamArgs a) {
 
 // chunk symbol counts (zero after the first terminated chunk) -> lens array for scan_lens_kernel
 __global__ void __launch_bounds__(256) stream_counts_kernel(StreamArgs a, uint64_t *lens) {
+    if (stream_gate_closed(a)) return;
     const uint64_t first_term = a.control[1];
     for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < a.num_chunks;
          k += (uint64_t)gridDim.x * blockDim.x)
@@ -800,6 +1002,7 @@ __global__ void __launch_bounds__(256) stream_counts_kernel(StreamArgs a, uint64
 
 // Final pass: every chunk up to the terminating one decodes again, now writing.
 __global__ void __launch_bounds__(kStreamThreads) stream_write_kernel(StreamArgs a, BatchView b) {
+    if (stream_gate_closed(a)) return;
     extern __shared__ uint32_t s_lut[];  // [LUT][stage]
     uint32_t *s_in = s_lut + a.lut_count;
     for (uint32_t i = threadIdx.x; i < a.lut_count; i += kStreamThreads) s_lut[i] = a.lut[i];
@@ -836,6 +1039,213 @@ __global__ void __launch_bounds__(kStreamThreads) stream_write_kernel(StreamArgs
                 leftover_state(a.in_aligned + (a.begin_bit >> 3), (a.end_bit - a.begin_bit) >> 3, cbits,
                                r.term == kTermUnknown, b.consumed, b.leftover_working_bits, b.leftover_num_bits);
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// One long stream, fused single pass (the normal path; the kernels above remain as the fallback for
+// inputs that do not behave, see stream_fused_verify_kernel).
+//
+// Persistent 256-thread blocks, one chunk per thread, tiles of 256 chunks taken from a ticket:
+//   1. stage the tile's chunks (+ the chunk before) in shared memory
+//   2. every thread pre-rolls to find its entry point and decodes its chunk ONCE, emitting the symbols
+//      byte by byte into a private shared-memory row
+//   3. chunks whose entry differs from their predecessor's exit are decoded again from there until the
+//      tile is consistent (block-local; 0.6 % of the chunks on HPACK text). The tile's FIRST chunk cannot
+//      be checked against the previous tile here; it pre-rolls over the whole previous chunk instead and
+//      records (entry, exit of the last chunk) for stream_fused_verify_kernel
+//   4. block scan of the symbol counts + decoupled look-back -> output offset of the tile
+//   5. rows -> dense image in shared memory (aligned like the global destination) -> 128-bit stores
+// The last chunk of the stream absorbs a tail of fewer than 32 bits, so "the stream ended" can only
+// be seen by the last chunk. Anything else that stops early (a window that matches no code) raises the
+// `fail` flag, and so does a tile whose first chunk did not enter where the previous tile left; the
+// fallback kernels then redo the stream (they return at once when the flag is clear).
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t kFusedRowSlack = 12;  // bytes: up to 31 / min_len symbols of the absorbed tail, and alignment
+
+struct StreamFusedArgs {
+    StreamArgs s;            // num_chunks counts the FUSED chunks: max(1, ceil((end_bit - 31) / kChunkBits))
+    BatchView b;
+    uint64_t *tile_state;    // look-back descriptors, one per tile
+    uint32_t *ticket;
+    uint64_t *tile_rec;      // per tile: [15:0] entry of its first chunk, [31:16] exit of its last, [33:32] term of its last
+    uint32_t *fail;
+    uint32_t num_tiles;
+    uint32_t row_words;      // row stride in words (odd)
+};
+
+__device__ __forceinline__ uint64_t fused_chunk_stop(const StreamArgs &a, uint64_t k) {
+    return k + 1 == a.num_chunks ? a.end_bit : (k + 1) * kChunkBits;
+}
+
+__global__ void __launch_bounds__(kStreamThreads, 2) stream_fused_kernel(StreamFusedArgs f) {
+    extern __shared__ __align__(16) uint32_t s_lut[];  // [LUT][stage][rows]
+    const StreamArgs &a = f.s;
+    const uint32_t lut_pad = (a.lut_count + 3u) & ~3u;
+    uint32_t *s_in = s_lut + lut_pad;
+    uint8_t *const s_dense = reinterpret_cast<uint8_t *>(s_in);
+    constexpr uint32_t kStageBytes = (kStreamStageWords * 4 + 15u) & ~15u;
+    uint8_t *const s_rows = s_dense + kStageBytes;
+    const uint32_t row_bytes = f.row_words * 4;
+    __shared__ uint16_t s_entry[kStreamThreads], s_exit[kStreamThreads];
+    __shared__ uint32_t s_nsym[kStreamThreads], s_off[kStreamThreads];
+    __shared__ uint8_t s_term[kStreamThreads];
+    __shared__ uint32_t s_warp_sum[kStreamThreads / 32];
+    __shared__ uint64_t s_prefix;
+    __shared__ uint32_t s_tile, s_first_term, s_total;
+
+    for (uint32_t i = threadIdx.x; i < a.lut_count; i += kStreamThreads) s_lut[i] = a.lut[i];
+    const uint32_t k = threadIdx.x, lane = lane_id(), warp = threadIdx.x >> 5;
+    const uint32_t row_addr = (uint32_t)__cvta_generic_to_shared(s_rows) + k * row_bytes;
+
+    while (true) {
+        __syncthreads();  // previous tile fully done (and the LUT is in place on the first trip)
+        if (k == 0) {
+            s_tile = atomicAdd(f.ticket, 1u);
+            s_first_term = kStreamThreads;
+        }
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile >= f.num_tiles) break;
+        const uint64_t c0 = (uint64_t)tile * kStreamThreads;
+        stream_stage(a, c0, s_in);
+        __syncthreads();
+
+        // ---- decode my chunk -------------------------------------------------------------------------------------
+        const uint64_t chunk = c0 + k;
+        const bool valid = chunk < a.num_chunks;
+        const uint64_t origin = (c0 - 1) * kChunkBits;  // wraps for c0 == 0; differences below stay exact
+        const uint64_t begin = chunk * kChunkBits;
+        const uint64_t stop = valid ? fused_chunk_stop(a, chunk) : begin;
+        const uint32_t s_begin = (uint32_t)(begin - origin), s_stop = (uint32_t)(stop - origin);
+        const uint32_t s_end = (uint32_t)min(a.end_bit - origin, (uint64_t)(kStreamThreads + 2) * kChunkBits);
+        const bool exact = begin <= a.begin_bit;  // the stream starts inside this chunk (or after it)
+        uint32_t entry = 0, exit = 0, nsym = 0, term = kTermStop;
+        uint32_t last_pos = 0;  // stage position after my last symbol (item-level results of the last chunk)
+        if (valid) {
+            if (exact) {
+                entry = (uint32_t)(a.begin_bit - begin);
+            } else {
+                // the first chunk of a tile cannot be checked in here: it pre-rolls over the whole chunk before it
+                const uint64_t roll = k == 0 ? kChunkBits : kPrerollBits;
+                const uint64_t from = max(begin - roll, a.begin_bit);
+                const SpanS pre = decode_span_smem<false, true, true>(
+                    s_in, s_lut, a.root_bits, (uint32_t)(from - origin), s_begin, s_end, 0u);
+                entry = pre.pos >= s_begin ? pre.pos - s_begin : 0u;
+            }
+            const SpanS r = decode_span_smem<true, true, false>(s_in, s_lut, a.root_bits, s_begin + entry, s_stop, s_end, row_addr);
+            exit = r.term == kTermStop ? r.pos - s_stop : 0u;
+            nsym = r.nsym;
+            term = r.term;
+            last_pos = r.pos;
+        }
+        s_entry[k] = (uint16_t)entry;
+        s_exit[k] = (uint16_t)exit;
+        s_nsym[k] = nsym;
+        s_term[k] = (uint8_t)term;
+        __syncthreads();
+
+        // ---- make the tile consistent ----------------------------------------------------------------------------
+        while (true) {
+            bool redo = false;
+            uint32_t want = 0;
+            if (valid && k > 0 && !exact && s_term[k - 1] == kTermStop && s_entry[k] != s_exit[k - 1]) {
+                redo = true;
+                want = s_exit[k - 1];
+            }
+            if (!__syncthreads_or(redo)) break;
+            if (redo) {
+                const SpanS r = decode_span_smem<true, true, false>(s_in, s_lut, a.root_bits, s_begin + want, s_stop, s_end, row_addr);
+                s_entry[k] = (uint16_t)want;
+                s_exit[k] = (uint16_t)(r.term == kTermStop ? r.pos - s_stop : 0u);
+                s_nsym[k] = r.nsym;
+                s_term[k] = (uint8_t)r.term;
+                last_pos = r.pos;
+            }
+            __syncthreads();
+        }
+        if (valid && s_term[k] != kTermStop) atomicMin(&s_first_term, k);
+        __syncthreads();
+        const uint32_t first_term = s_first_term;
+        // something stopped before the stream's last chunk: not for this kernel
+        if (first_term < kStreamThreads && c0 + first_term + 1 < a.num_chunks && k == 0) atomicExch(f.fail, 1u);
+        if (k == 0) {
+            const uint32_t nvalid = (uint32_t)min((uint64_t)kStreamThreads, a.num_chunks - c0);
+            f.tile_rec[tile] = (uint64_t)s_entry[0] | ((uint64_t)s_exit[nvalid - 1] << 16) | ((uint64_t)s_term[nvalid - 1] << 32);
+        }
+
+        // ---- offsets: block scan + look-back -------------------------------------------------------------------
+        const uint32_t cnt = (valid && k <= first_term) ? s_nsym[k] : 0u;
+        const uint32_t incl = warp_inclusive_scan(cnt);
+        if (lane == 31) s_warp_sum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t w = lane < kStreamThreads / 32 ? s_warp_sum[lane] : 0u;
+            const uint32_t wi = warp_inclusive_scan(w);
+            if (lane < kStreamThreads / 32) s_warp_sum[lane] = wi - w;
+            const uint32_t total = __shfl_sync(0xffffffffu, wi, kStreamThreads / 32 - 1);
+            const uint64_t prefix = lookback_exclusive_prefix(f.tile_state, tile, total);
+            if (lane == 0) {
+                s_prefix = prefix;
+                s_total = total;
+            }
+        }
+        __syncthreads();
+        const uint64_t tile_base = s_prefix;
+        const uint32_t off = s_warp_sum[warp] + incl - cnt;
+        s_off[k] = off;
+
+        // ---- item-level results (n == 1): the stream's last chunk ----------------------------------------------
+        if (valid && chunk + 1 == a.num_chunks) {
+            const uint32_t my_term = s_term[k];
+            const uint64_t total = tile_base + off + cnt;
+            const uint64_t cbits = (uint64_t)last_pos + origin - a.begin_bit;  // stream bits turned into symbols
+            const BatchView &b = f.b;
+            b.out_offsets[0] = 0;
+            b.out_offsets[1] = total;
+            if (b.out_lens) b.out_lens[0] = total;
+            if (b.status) b.status[0] = my_term == kTermUnknown ? kStatusUnknownSymbol : kStatusOk;
+            if (b.consumed || b.leftover_working_bits || b.leftover_num_bits)
+                leftover_state(a.in_aligned + (a.begin_bit >> 3), (a.end_bit - a.begin_bit) >> 3, cbits,
+                               my_term == kTermUnknown, b.consumed, b.leftover_working_bits, b.leftover_num_bits);
+        }
+        __syncthreads();  // s_off complete; everybody is done with the stage
+
+        // ---- rows -> dense image (aligned like the global destination) -> global ----------------------------------
+        {
+            const BatchView &b = f.b;
+            const uint32_t total = s_total;
+            const uint32_t pad = (uint32_t)((reinterpret_cast<uintptr_t>(b.out) + tile_base) & 15);
+            // rows that start before `front` lie where the dense image may grow: they go first (their destination
+            // ends inside the stage area); the image (<= 256 rows) ends before row offset `front` + stage
+            const uint32_t front = kStageBytes - row_bytes - 32;
+            const uint32_t row_off = k * row_bytes;
+#pragma unroll 1
+            for (int phase = 0; phase < 2; ++phase) {
+                if ((row_off < front) == (phase == 0)) smem_copy_row(s_rows + row_off, s_dense + pad + off, cnt);
+                __syncthreads();
+            }
+            const uint64_t room = tile_base < b.out_capacity ? b.out_capacity - tile_base : 0;
+            const uint32_t ncopy = (uint32_t)min((uint64_t)total, room);
+            uint8_t *const g0 = b.out + tile_base;
+            const uint32_t head = min(ncopy, (16u - pad) & 15u);
+            const uint32_t nvec = (ncopy - head) >> 4;
+            const uint4 *sv = reinterpret_cast<const uint4 *>(s_dense + pad + head);
+            uint4 *gv = reinterpret_cast<uint4 *>(g0 + head);
+            for (uint32_t v = k; v < nvec; v += kStreamThreads) gv[v] = sv[v];
+            if (k < head) g0[k] = s_dense[pad + k];
+            const uint32_t tail0 = head + 16 * nvec;
+            if (k >= 32 && k - 32 < ncopy - tail0) g0[tail0 + k - 32] = s_dense[pad + tail0 + k - 32];
+        }
+    }
+}
+
+// Every tile's first chunk must have entered exactly where the previous tile's last chunk left.
+__global__ void __launch_bounds__(256) stream_fused_verify_kernel(StreamFusedArgs f) {
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x + 1; t < f.num_tiles; t += gridDim.x * blockDim.x) {
+        const uint64_t prev = f.tile_rec[t - 1], mine = f.tile_rec[t];
+        const uint32_t prev_exit = (uint32_t)(prev >> 16) & 0xffffu, prev_term = (uint32_t)(prev >> 32) & 3u;
+        if (prev_term != kTermStop || (uint32_t)(mine & 0xffffu) != prev_exit) atomicExch(f.fail, 1u);
     }
 }
 

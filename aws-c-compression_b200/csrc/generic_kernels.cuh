@@ -261,7 +261,9 @@ constexpr int kScanItemsPerThread = 8;
 constexpr int kScanTile = kScanThreads * kScanItemsPerThread;
 
 __global__ void __launch_bounds__(kScanThreads)
-    scan_lens_kernel(const uint64_t *lens, uint64_t *offsets, uint64_t n, uint64_t *tile_state, uint32_t *ticket) {
+    scan_lens_kernel(const uint64_t *lens, uint64_t *offsets, uint64_t n, uint64_t *tile_state, uint32_t *ticket,
+                     const uint32_t *gate = nullptr) {
+    if (gate != nullptr && *gate == 0) return;  // (fallback of the fused stream decoder: nothing to redo)
     __shared__ uint32_t s_tile;
     __shared__ uint64_t s_warp_sums[kScanThreads / 32];
     __shared__ uint64_t s_tile_prefix;

@@ -70,9 +70,9 @@ struct GrowBuf {
 };
 // Per-launch kernel scratch (tile descriptors, chunk records, ...). One per concurrent stream.
 struct Scratch {
-    GrowBuf lens, tile_state, tile_first, chunks, chunk_lens, chunk_offsets;
+    GrowBuf lens, tile_state, tile_first, chunks, chunk_lens, chunk_offsets, fused;
     void release() {
-        GrowBuf *all[] = {&lens, &tile_state, &tile_first, &chunks, &chunk_lens, &chunk_offsets};
+        GrowBuf *all[] = {&lens, &tile_state, &tile_first, &chunks, &chunk_lens, &chunk_offsets, &fused};
         for (GrowBuf *g : all) g->release();
     }
 };
@@ -159,14 +159,15 @@ hb::BatchView make_view(const aws_huffman_batch *b) {
 
 // lens -> offsets on the device
 int launch_scan(
-    aws_huffman_batch_ctx *ctx, Scratch &sc, const uint64_t *lens, uint64_t *offsets, uint64_t n, cudaStream_t stream) {
+    aws_huffman_batch_ctx *ctx, Scratch &sc, const uint64_t *lens, uint64_t *offsets, uint64_t n, cudaStream_t stream,
+    const uint32_t *gate = nullptr) {
     const uint64_t tiles = std::max<uint64_t>(1, (n + kScanTile - 1) / kScanTile);
     const size_t state_bytes = tiles * sizeof(uint64_t) + 256;
     HB_CUDA_TRY(sc.tile_state.reserve(state_bytes));
     HB_CUDA_TRY(cudaMemsetAsync(sc.tile_state.ptr, 0, state_bytes, stream));
     uint64_t *state = sc.tile_state.as<uint64_t>();
     uint32_t *ticket = reinterpret_cast<uint32_t *>(state + tiles);
-    scan_lens_kernel<<<(unsigned)tiles, kScanThreads, 0, stream>>>(lens, offsets, n, state, ticket);
+    scan_lens_kernel<<<(unsigned)tiles, kScanThreads, 0, stream>>>(lens, offsets, n, state, ticket, gate);
     ++ctx->launches;
     HB_CUDA_TRY(cudaGetLastError());
     return AWS_OP_SUCCESS;
@@ -268,19 +269,37 @@ int decode_batch_fast(aws_huffman_batch_ctx *ctx, Scratch &sc, const hb::BatchVi
     a.lut = ctx->tables.lut;
     a.lut_count = ctx->tables.lut_count;
     a.root_bits = ctx->tables.lut_root_bits;
+    a.min_len = std::max<uint32_t>(1, ctx->tables.min_len);
     a.tile_state = sc.tile_state.as<uint64_t>();
     a.ticket = reinterpret_cast<uint32_t *>(a.tile_state + num_tiles);
     a.num_tiles = (uint32_t)num_tiles;
-    const size_t smem = ((size_t)ctx->tables.lut_count + kDecStageWords + 2) * sizeof(uint32_t);
+    // Shared memory of one block (two blocks per SM): [LUT][stage][rows]. A string of L bytes decodes to at
+    // most 8 L / min_len symbols, so the row area is that much larger than the stage; and the dense output
+    // image (which reuses the stage and the front of the rows) must end before row offset `front`
+    // (decode_batch_kernel step 4): rows <= stage + front - 32.
+    const size_t lut_bytes = (((size_t)a.lut_count + 3) & ~size_t(3)) * 4;
+    const size_t budget = (size_t)108 * 1024 - 6 * 1024 /* static */ - lut_bytes;
+    const double expand = 8.0 / a.min_len;
+    size_t stage_bytes = (size_t)((double)budget / (1.0 + expand)) & ~size_t(15);
+    stage_bytes = std::max<size_t>(stage_bytes, 2 * kDecMaxRow);
+    size_t rows_bytes = budget - stage_bytes;
+    const size_t front = (stage_bytes - kDecMaxRow - 32) & ~size_t(3);
+    rows_bytes = std::min(rows_bytes, stage_bytes + front - 64) & ~size_t(15);
+    a.stage_words = (uint32_t)(stage_bytes / 4 - 2);
+    a.rows_bytes = (uint32_t)rows_bytes;
+    const size_t smem = lut_bytes + ((stage_bytes + 15) & ~size_t(15)) + rows_bytes + 64;
     HB_CUDA_TRY(cudaFuncSetAttribute(decode_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const unsigned blocks = (unsigned)std::min<uint64_t>(num_tiles, (uint64_t)ctx->sm_count * 4);
+    const unsigned blocks = (unsigned)std::min<uint64_t>(num_tiles, (uint64_t)ctx->sm_count * 2);
     decode_batch_kernel<<<blocks, kDecThreads, smem, stream>>>(a);
     ++ctx->launches;
     HB_CUDA_TRY(cudaGetLastError());
     return AWS_OP_SUCCESS;
 }
 
-// Packed layout, one long stream: chunked speculative decode.
+// Packed layout, one long stream: chunked speculative decode. The fused single-pass kernel does the
+// work; the multi-kernel path behind it only runs (on the device's own decision, no host round trip)
+// when the fused kernel raised its `fail` flag: a stream that does not self-synchronise, or that stops
+// at an unknown symbol before its end.
 int decode_stream_fast(
     aws_huffman_batch_ctx *ctx, Scratch &sc, const hb::BatchView &v, uint64_t len, cudaStream_t stream) {
     const uint64_t lead = reinterpret_cast<uintptr_t>(v.in) & 15;  // "aligned space" starts on a 16-byte boundary
@@ -300,14 +319,51 @@ int decode_stream_fast(
     a.lut = ctx->tables.lut;
     a.lut_count = ctx->tables.lut_count;
     a.root_bits = ctx->tables.lut_root_bits;
-    HB_CUDA_TRY(cudaMemsetAsync(a.control, 0xff, 2 * sizeof(uint64_t), stream));
     const size_t smem = ctx->tables.lut_count * sizeof(uint32_t);
     const size_t smem_staged = smem + kStreamStageWords * sizeof(uint32_t);
+
+    // ---- fused single pass ------------------------------------------------------------------------------------
+    const uint32_t min_len = std::max<uint32_t>(1, ctx->tables.min_len);
+    const uint32_t row_words = (((kChunkBits + 31) / min_len + 4 + 3) / 4) | 1u;
+    const size_t lut_bytes = (((size_t)ctx->tables.lut_count + 3) & ~size_t(3)) * 4;
+    const size_t stage_bytes = (kStreamStageWords * 4 + 15) & ~size_t(15);
+    const size_t fused_smem = lut_bytes + stage_bytes + (size_t)kStreamThreads * row_words * 4 + 16;
+    // (the dense output image reuses the stage and the front of the rows: stream_fused_kernel step 5)
+    const bool fused = (size_t)kStreamThreads * row_words * 4 + 16 <= 2 * stage_bytes - row_words * 4 - 32 &&
+                       fused_smem <= 110 * 1024 && !getenv("AWS_HUFFMAN_BATCH_NO_FUSED_STREAM");
+    if (fused) {
+        StreamFusedArgs f{};
+        f.s = a;
+        f.s.num_chunks = std::max<uint64_t>(1, (end_bit > 31 ? end_bit - 31 + kChunkBits - 1 : 0) / kChunkBits);
+        f.b = v;
+        f.num_tiles = (uint32_t)((f.s.num_chunks + kStreamThreads - 1) / kStreamThreads);
+        f.row_words = row_words;
+        // [tile_state: num_tiles][tile_rec: num_tiles][ticket][fail]
+        const size_t words = 2 * (size_t)f.num_tiles + 2;
+        HB_CUDA_TRY(sc.fused.reserve(words * sizeof(uint64_t)));
+        HB_CUDA_TRY(cudaMemsetAsync(sc.fused.ptr, 0, words * sizeof(uint64_t), stream));
+        f.tile_state = sc.fused.as<uint64_t>();
+        f.tile_rec = f.tile_state + f.num_tiles;
+        f.ticket = reinterpret_cast<uint32_t *>(f.tile_rec + f.num_tiles);
+        f.fail = f.ticket + 2;
+        a.gate = f.fail;
+        HB_CUDA_TRY(cudaFuncSetAttribute(stream_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem));
+        const unsigned blocks = (unsigned)std::min<uint64_t>(f.num_tiles, (uint64_t)ctx->sm_count * 2);
+        stream_fused_kernel<<<blocks, kStreamThreads, fused_smem, stream>>>(f);
+        stream_fused_verify_kernel<<<(unsigned)std::min<uint64_t>((f.num_tiles + 255) / 256, 1024), 256, 0, stream>>>(f);
+        ctx->launches += 2;
+        HB_CUDA_TRY(cudaGetLastError());
+    }
+
+    // ---- multi-kernel path (alone, or gated behind the fused kernel's fail flag) ----------------------------------
+    HB_CUDA_TRY(cudaMemsetAsync(a.control, 0xff, 2 * sizeof(uint64_t), stream));
     HB_CUDA_TRY(cudaFuncSetAttribute(stream_sync_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_staged));
     HB_CUDA_TRY(cudaFuncSetAttribute(stream_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_staged));
-    const unsigned wide = (unsigned)std::min<uint64_t>((num_chunks + kStreamThreads - 1) / kStreamThreads,
-                                                       (uint64_t)ctx->sm_count * 12);
-    const unsigned flat = (unsigned)std::min<uint64_t>((num_chunks + 255) / 256, (uint64_t)ctx->sm_count * 8);
+    // a gated launch that finds the flag clear costs a few microseconds: keep those grids small
+    const uint64_t cap_wide = fused ? (uint64_t)ctx->sm_count * 4 : (uint64_t)ctx->sm_count * 12;
+    const uint64_t cap_flat = fused ? (uint64_t)ctx->sm_count * 4 : (uint64_t)ctx->sm_count * 8;
+    const unsigned wide = (unsigned)std::min<uint64_t>((num_chunks + kStreamThreads - 1) / kStreamThreads, cap_wide);
+    const unsigned flat = (unsigned)std::min<uint64_t>((num_chunks + 255) / 256, cap_flat);
     stream_sync_kernel<<<wide, kStreamThreads, smem_staged, stream>>>(a);
     for (int round = 0; round < 2; ++round) stream_fix_kernel<<<wide, kStreamThreads, smem, stream>>>(a);
     stream_verify_kernel<<<flat, 256, 0, stream>>>(a);
@@ -315,7 +371,7 @@ int decode_stream_fast(
     stream_counts_kernel<<<flat, 256, 0, stream>>>(a, sc.chunk_lens.as<uint64_t>());
     ctx->launches += 6;
     HB_CUDA_TRY(cudaGetLastError());
-    if (launch_scan(ctx, sc, sc.chunk_lens.as<uint64_t>(), a.chunk_offsets, num_chunks, stream)) return AWS_OP_ERR;
+    if (launch_scan(ctx, sc, sc.chunk_lens.as<uint64_t>(), a.chunk_offsets, num_chunks, stream, a.gate)) return AWS_OP_ERR;
     stream_write_kernel<<<wide, kStreamThreads, smem_staged, stream>>>(a, v);
     ++ctx->launches;
     HB_CUDA_TRY(cudaGetLastError());
@@ -371,7 +427,7 @@ int lane_prepare(Lane &lane) {
 }
 
 constexpr uint64_t kPipelineMinBytes = 8ull << 20;   // below this one shot is as good
-constexpr uint64_t kPipelineShardBytes = 16ull << 20;
+constexpr uint64_t kPipelineShardBytes = 8ull << 20;  // measured best on PCIe Gen5 x16 (tools/e2e_sweep.sh)
 
 // Packed layout with many items: the batch is cut into sub-batches (contiguous item ranges balanced by
 // bytes) that flow through kLanes lanes, so the host->device copy of one sub-batch, the kernels of the
@@ -391,13 +447,6 @@ int run_host_batch_pipelined(aws_huffman_batch_ctx *ctx, const aws_huffman_batch
 
     for (Lane &lane : ctx->lanes)
         if (lane_prepare(lane)) return AWS_OP_ERR;
-    if (!ctx->offsets_ready) HB_CUDA_TRY(cudaEventCreateWithFlags(&ctx->offsets_ready, cudaEventDisableTiming));
-
-    // all input offsets go up once; sub-batches rebase their slice on the device
-    HB_CUDA_TRY(ctx->s_in_off.reserve((n + 1) * sizeof(uint64_t)));
-    HB_CUDA_TRY(cudaMemcpyAsync(
-        ctx->s_in_off.ptr, b->in_offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
-    HB_CUDA_TRY(cudaEventRecord(ctx->offsets_ready, ctx->stream));
 
     const uint32_t max_len = std::max<uint32_t>(1, ctx->tables.max_len);
     const uint32_t min_len = std::max<uint32_t>(1, ctx->tables.min_len);
@@ -424,11 +473,13 @@ int run_host_batch_pipelined(aws_huffman_batch_ctx *ctx, const aws_huffman_batch
         if (encode ? b->overflow_num_bits != nullptr : b->leftover_num_bits != nullptr) HB_CUDA_TRY(lane.aux8.reserve(nj));
         if (!encode && b->leftover_working_bits) HB_CUDA_TRY(lane.aux64.reserve(nj * sizeof(uint64_t)));
 
-        HB_CUDA_TRY(cudaStreamWaitEvent(lane.stream, ctx->offsets_ready, 0));
+        // the sub-batch's slice of the offsets goes up with it and is rebased in place on the device
+        HB_CUDA_TRY(cudaMemcpyAsync(
+            lane.in_off.ptr, b->in_offsets + a, (nj + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, lane.stream));
         if (bytes_in)
             HB_CUDA_TRY(cudaMemcpyAsync(lane.in.ptr, b->in + in0, bytes_in, cudaMemcpyHostToDevice, lane.stream));
         rebase_offsets_kernel<<<(unsigned)((nj + 1 + 255) / 256), 256, 0, lane.stream>>>(
-            ctx->s_in_off.as<uint64_t>() + a, nj + 1, in0, lane.in_off.as<uint64_t>());
+            lane.in_off.as<uint64_t>(), nj + 1, in0, lane.in_off.as<uint64_t>());
         ++ctx->launches;
         hb::BatchView v{};
         v.n = nj;
