@@ -421,95 +421,151 @@ __device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) {
     asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
-// Returns kTermStop, or kTermUnknown when a window with >= 32 real bits matched no code (!kSkipHoles).
-template <bool kEmit, bool kPadded, bool kSkipHoles>
-__device__ __forceinline__ uint32_t decode_pairs(
-    const uint32_t *s_in, const uint32_t *s_lut, uint32_t root_bits, uint32_t &pos, uint32_t pair_end, uint32_t &out_addr) {
-    constexpr int kSteps = 6;
-    constexpr uint32_t kParked = 0x80000000u;  // positions are far below 2^31: a parked lane fails "pos < pair_end"
-    if (pos >= pair_end) return kTermStop;
-    uint32_t in_addr = (uint32_t)__cvta_generic_to_shared(s_in);
-    uint32_t lut_addr = (uint32_t)__cvta_generic_to_shared(s_lut);
-    // (opaque copy: otherwise the compiler re-derives the base from the shared window in every step)
-    asm volatile("mov.u32 %0, %0;" : "+r"(lut_addr));
-    const uint32_t shift = 32 - root_bits;
-    // The stream words under the cursor live in registers: w0 holds bit `pos`, w1 the word after it, w2 is
-    // fetched one word ahead, so the dependent chain of a step is funnel -> LUT load -> add and the stream
-    // loads are off it. A span never leaves its padded row in here (the callers' spans end at a row
-    // boundary and pair_end lies 12+ bits before it), so the words are consecutive in shared memory.
-    uint32_t wa = in_addr + (kPadded ? (pos >> 5) + (pos >> 10) : (pos >> 5)) * 4;
-    uint32_t w0 = lds_u32(wa), w1 = lds_u32(wa + 4), w2 = lds_u32(wa + 8);
-    wa += 12;
-    int limit = (int)((pos | 31u) + 1u);  // first bit after w0
-    while (pos < pair_end) {
-#pragma unroll
-        for (int step = 0; step < kSteps; ++step) {
-            if (pos < pair_end) {
-                const uint32_t e = lds_u32(lut_addr + ((__funnelshift_l(w1, w0, pos) >> shift) << 2));
-                if (dlut_is_leaf(e)) {
-                    pos += e >> 24;
-                    if (kEmit) {
-                        sts_u8(out_addr, e >> 8);
-                        sts_u8(out_addr + 1, e >> 16);
-                        out_addr += e & 3u;
-                    }
-                } else {
-                    pos |= kParked;
-                }
-                if ((int)pos >= limit) {  // (a parked position is negative)
-                    w0 = w1;
-                    w1 = w2;
-                    w2 = lds_u32(wa);
-                    wa += 4;
-                    limit += 32;
-                }
-            }
-        }
-        if (pos & kParked) {
-            pos &= ~kParked;
-            const uint32_t window = __funnelshift_l(w1, w0, pos);
-            const uint32_t e = dec_walk(s_lut, root_bits, window, s_lut[window >> shift]);
-            if (e == 0) {
-                if (!kSkipHoles) return kTermUnknown;
-                ++pos;
-            } else {
-                pos += dlut_len1(e);
-                if (kEmit) {
-                    sts_u8(out_addr, e >> 8);
-                    ++out_addr;
-                }
-            }
-            if ((int)pos >= limit) {
-                w0 = w1;
-                w1 = w2;
-                w2 = lds_u32(wa);
-                wa += 4;
-                limit += 32;
-            }
+// The stream words under the cursor live in registers: w0 holds bit `pos`, w1 the word after it, w2 is
+// fetched one word ahead, so the dependent chain of a step is funnel -> LUT load -> add and the stream
+// loads are off it. A span never leaves its padded row in here (the callers' spans end at a row boundary,
+// or fewer than 32 bits after one), so the words are consecutive in shared memory.
+struct StreamCursor {
+    uint32_t w0, w1, w2;
+    uint32_t wa;  // shared-window address of the word after w2
+    int limit;    // first bit position after w0
+    template <bool kPadded>
+    __device__ __forceinline__ void init(uint32_t in_addr, uint32_t pos) {
+        wa = in_addr + (kPadded ? (pos >> 5) + (pos >> 10) : (pos >> 5)) * 4;
+        w0 = lds_u32(wa);
+        w1 = lds_u32(wa + 4);
+        w2 = lds_u32(wa + 8);
+        wa += 12;
+        limit = (int)((pos | 31u) + 1u);
+    }
+    __device__ __forceinline__ uint32_t window(uint32_t pos) const { return __funnelshift_l(w1, w0, pos); }
+    // after `pos` moved forward by at most 32 bits
+    __device__ __forceinline__ void follow(uint32_t pos) {
+        if ((int)pos >= limit) {
+            w0 = w1;
+            w1 = w2;
+            w2 = lds_u32(wa);
+            wa += 4;
+            limit += 32;
         }
     }
-    return kTermStop;
-}
+};
 
-// A span decoded by decode_pairs + decode_smem's careful tail. nsym is only meaningful when emitting.
+// Decodes stage bits from `pos` until `stop`; the stream itself ends at `end` (stop <= end; stage-relative
+// bit positions). Same rules and results as decode_smem (which follows the reference loop); symbols go
+// to the shared-memory row at out_addr when kEmit. nsym is only meaningful when emitting.
 template <bool kEmit, bool kPadded, bool kSkipHoles>
 __device__ __forceinline__ SpanS decode_span_smem(
     const uint32_t *s_in, const uint32_t *s_lut, uint32_t root_bits, uint32_t pos, uint32_t stop, uint32_t end,
     uint32_t out_addr) {
-    const uint32_t fast_end = (end >= 32u) ? min(stop, end - 31u) : 0u;
-    const uint32_t pair_end = fast_end > root_bits ? fast_end - root_bits : 0u;
+    constexpr int kSteps = 6;
+    constexpr uint32_t kParked = 0x80000000u;  // positions are far below 2^31: a parked lane fails "pos < pair_end"
     const uint32_t out0 = out_addr;
-    if (decode_pairs<kEmit, kPadded, kSkipHoles>(s_in, s_lut, root_bits, pos, pair_end, out_addr) == kTermUnknown) {
-        SpanS r;
-        r.pos = pos;
-        r.nsym = out_addr - out0;
-        r.term = kTermUnknown;
-        return r;
+    SpanS r;
+    r.term = kTermStop;
+    if (pos < stop) {
+        // two symbols per lookup while at least 32 real bits follow and even the second symbol is sure to
+        // start before `stop`
+        const uint32_t fast_end = (end >= 32u) ? min(stop, end - 31u) : 0u;
+        const uint32_t pair_end = fast_end > root_bits ? fast_end - root_bits : 0u;
+        const uint32_t in_addr = (uint32_t)__cvta_generic_to_shared(s_in);
+        uint32_t lut_addr = (uint32_t)__cvta_generic_to_shared(s_lut);
+        // (opaque copy: otherwise the compiler re-derives the base from the shared window in every step)
+        asm volatile("mov.u32 %0, %0;" : "+r"(lut_addr));
+        const uint32_t shift = 32 - root_bits;
+        StreamCursor c;
+        c.init<kPadded>(in_addr, pos);
+        while (pos < pair_end) {
+            // Straight-line steps: a lane that is parked or past its end runs along with every update
+            // predicated off (its lookup reads some valid root entry and is ignored), so the warp never
+            // splits inside a round.
+#pragma unroll
+            for (int step = 0; step < kSteps; ++step) {
+                const uint32_t e = lds_u32(lut_addr + ((c.window(pos) >> shift) << 2));
+                const bool active = pos < pair_end;
+                const bool adv = active && dlut_is_leaf(e);
+                if (active && !dlut_is_leaf(e)) pos |= kParked;
+                if (adv) pos += e >> 24;
+                if (kEmit) {
+                    const uint32_t on = adv ? 1u : 0u;
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p st.shared.u8 [%0], %1;\n\t@p st.shared.u8 [%0+1], %2;\n\t}" ::"r"(out_addr),
+                        "r"(e >> 8), "r"(e >> 16), "r"(on)
+                        : "memory");
+                    if (adv) out_addr += e & 3u;
+                }
+                const bool cross = adv && (int)pos >= c.limit;
+                if (cross) {
+                    c.w0 = c.w1;
+                    c.w1 = c.w2;
+                    c.limit += 32;
+                }
+                {
+                    const uint32_t on = cross ? 1u : 0u;
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.shared.u32 %0, [%1];\n\t}"
+                                 : "+r"(c.w2)
+                                 : "r"(c.wa), "r"(on));
+                }
+                if (cross) c.wa += 4;
+            }
+            // codes longer than the root index (a few % of the symbols): the parked lanes walk the sub-tables
+            // together, once per round
+            if (pos & kParked) {
+                pos &= ~kParked;
+                const uint32_t window = c.window(pos);
+                const uint32_t e = dec_walk(s_lut, root_bits, window, s_lut[window >> shift]);
+                if (e == 0) {
+                    if (!kSkipHoles) {
+                        r.term = kTermUnknown;  // >= 32 real bits and no code matches
+                        break;
+                    }
+                    ++pos;
+                } else {
+                    pos += dlut_len1(e);
+                    if (kEmit) {
+                        sts_u8(out_addr, e >> 8);
+                        ++out_addr;
+                    }
+                }
+                c.follow(pos);
+            }
+        }
+        // the last few symbols of the span: one lookup at a time with the end-of-stream rules (the window is
+        // the stream zero-extended, huffman.c:196-211; a code that does not fit ends the stream, :240-255).
+        // A two-symbol entry still counts when its second code starts before `stop` and ends inside the stream.
+        while (r.term == kTermStop && pos < stop) {
+            const uint32_t left = end - pos;  // >= 1
+            uint32_t window = c.window(pos);
+            if (left < 32u) window &= 0xffffffffu << (32u - left);
+            uint32_t e = lds_u32(lut_addr + ((window >> shift) << 2));
+            if (e != 0 && !dlut_is_leaf(e)) e = dec_walk(s_lut, root_bits, window, e);
+            if (e == 0) {
+                if (kSkipHoles && left > 1u) {
+                    ++pos;
+                    c.follow(pos);
+                    continue;
+                }
+                r.term = left < 32u ? kTermEnd : kTermUnknown;  // fewer than 32 bits left: padding
+                break;
+            }
+            const uint32_t len1 = dlut_len1(e);
+            if (len1 > left) {
+                r.term = kTermEnd;  // a code cut short by the end of the stream
+                break;
+            }
+            const bool two = dlut_count(e) == 2u && pos + len1 < stop && dlut_total_len(e) <= left;
+            if (kEmit) {
+                sts_u8(out_addr, e >> 8);
+                if (two) sts_u8(out_addr + 1, e >> 16);
+                out_addr += two ? 2u : 1u;
+            }
+            pos += two ? dlut_total_len(e) : len1;
+            c.follow(pos);
+        }
     }
-    ByteEmitter em;
-    em.addr = out_addr;
-    SpanS r = decode_smem<kEmit, kPadded, kSkipHoles>(s_in, s_lut, root_bits, pos, stop, end, &em);
-    r.nsym = em.addr - out0;
+    if (r.term == kTermStop && pos >= end) r.term = kTermEnd;
+    r.pos = pos;
+    r.nsym = out_addr - out0;
     return r;
 }
 
@@ -533,6 +589,7 @@ struct DecBatchArgs {
     uint64_t *tile_state;
     uint32_t *ticket;
     uint32_t num_tiles;
+    uint32_t debug;  // AWS_HUFFMAN_BATCH_EXPERIMENT (A/B timing only)
 };
 
 // Thread-serial copy of n bytes inside shared memory; src is 4-byte aligned, dst is not.
@@ -681,7 +738,14 @@ __global__ void __launch_bounds__(kDecThreads, 2) decode_batch_kernel(DecBatchAr
                 uint32_t nsym, term;
                 if (staged) {
                     const uint32_t ib = s_start[it], ie = ib + nbytes * 8;
-                    const SpanS r = decode_span_smem<true, false, false>(s_in, s_lut, a.root_bits, ib, ie, ie, rows_addr + s_row[it]);
+                    SpanS r;
+                    if (a.debug & 2u) {
+                        ByteEmitter em;
+                        em.addr = rows_addr + s_row[it];
+                        r = decode_smem<true, false, false>(s_in, s_lut, a.root_bits, ib, ie, ie, &em);
+                    } else {
+                        r = decode_span_smem<true, false, false>(s_in, s_lut, a.root_bits, ib, ie, ie, rows_addr + s_row[it]);
+                    }
                     cbits = r.pos - ib;
                     nsym = r.nsym;
                     term = r.term;

@@ -270,6 +270,7 @@ int decode_batch_fast(aws_huffman_batch_ctx *ctx, Scratch &sc, const hb::BatchVi
     a.lut_count = ctx->tables.lut_count;
     a.root_bits = ctx->tables.lut_root_bits;
     a.min_len = std::max<uint32_t>(1, ctx->tables.min_len);
+    if (const char *exp = getenv("AWS_HUFFMAN_BATCH_EXPERIMENT")) a.debug = (uint32_t)atoi(exp);
     a.tile_state = sc.tile_state.as<uint64_t>();
     a.ticket = reinterpret_cast<uint32_t *>(a.tile_state + num_tiles);
     a.num_tiles = (uint32_t)num_tiles;
