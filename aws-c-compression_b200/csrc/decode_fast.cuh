@@ -931,6 +931,24 @@ __device__ __forceinline__ void stream_stage(const StreamArgs &a, uint64_t c0, u
     const uint64_t nquads_valid = (end_byte + 15) >> 4;
     // rows 0..kStreamThreads hold 32 words (8 quads) each; word 32 of a row duplicates word 0 of the next
     constexpr uint32_t kQuads = (kStreamThreads + 1) * 8 + 1;
+    if (c0 >= 1 && ((c0 - 1) * 8 + kQuads) * 16 <= end_byte) {
+        // interior tile: every staged byte belongs to the stream
+        const uint4 *src = g4 + (c0 - 1) * 8;
+        for (uint32_t i = threadIdx.x; i < kQuads; i += kStreamThreads) {
+            const uint32_t row = i >> 3, col4 = i & 7;
+            const uint4 raw = __ldg(src + i);
+            const uint32_t v0 = __byte_perm(raw.x, 0, 0x0123);
+            if (row <= kStreamThreads) {
+                uint32_t *dst = s_in + row * kStreamRowWords + col4 * 4;
+                dst[0] = v0;
+                dst[1] = __byte_perm(raw.y, 0, 0x0123);
+                dst[2] = __byte_perm(raw.z, 0, 0x0123);
+                dst[3] = __byte_perm(raw.w, 0, 0x0123);
+            }
+            if (col4 == 0 && row > 0) s_in[(row - 1) * kStreamRowWords + 32] = v0;
+        }
+        return;
+    }
     for (uint32_t i = threadIdx.x; i < kQuads; i += kStreamThreads) {
         const uint32_t row = i >> 3, col4 = i & 7;
         const int64_t q = ((int64_t)c0 - 1 + row) * 8 + col4;  // aligned 16-byte index in the stream

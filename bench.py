@@ -137,17 +137,21 @@ def summarize_clocks(path):
             "samples": len(sm)}
 
 
-def profiled_traffic(workload, dominant):
+def profiled_traffic(workload, dominant, raw_bytes):
     """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
-    (profiles/r1_kernels.json, made by tools/ncu_summary.py), or None."""
+    (profiles/r1_kernels.json, made by tools/ncu_summary.py), or None. The stream capture was taken on a
+    256 MiB stream; traffic is proportional to the stream size, so it is scaled to this run's."""
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "r1_kernels.json")))
         group = prof["hpack_batch" if workload == "hpack_batch" else "stream_256MiB"]
-        want = {"encode": "encode_tiled", "decode": "decode_batch" if workload == "hpack_batch" else "stream_write"}[dominant]
+        want = {"encode": "encode_tiled", "decode": "decode_batch" if workload == "hpack_batch" else "stream_fused_kernel"}[dominant]
         for k in group:
             if want in k["kernel"]:
                 scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
-                return int(k["dram_read"] * scale[k["dram_read_unit"]] + k["dram_write"] * scale[k["dram_write_unit"]])
+                total = k["dram_read"] * scale[k["dram_read_unit"]] + k["dram_write"] * scale[k["dram_write_unit"]]
+                if workload != "hpack_batch":
+                    total *= raw_bytes / float(1 << 28)
+                return int(total)
     except Exception:
         pass
     return None
@@ -451,10 +455,10 @@ def main():
             "roofline": {"bound": "hbm",
                          "kernel": {"hpack_batch": {"encode": "encode_tiled_kernel<true>", "decode": "decode_batch_kernel"},
                                     "stream": {"encode": "encode_tiled_kernel<false>",
-                                               "decode": "stream_sync_kernel + stream_write_kernel (+ small helpers)"}}
+                                               "decode": "stream_fused_kernel (+ verify and gated fallback launches)"}}
                                    [args.workload][dominant] + " (per GPU; CUDA events around the " + dominant + " call)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": profiled_traffic(args.workload, dominant) if args.workload == "hpack_batch" else None,
+                         "traffic": profiled_traffic(args.workload, dominant, raw_bytes),
                          "algorithmic_bytes_per_launch": int(one_way),
                          "peak_source": peak_src, "frac_of_8000_nominal": achieved / 8000.0,
                          "encode_frac": enc_gbs / peak, "decode_frac": dec_gbs / peak},

@@ -430,3 +430,55 @@ def test_pipelined_host_path(contexts, oracle, oracle_tables, pkg):
     with pytest.raises(pkg.CodecError) as err:
         ctx.encode(data, offs, total - 1)
     assert err.value.code == pkg.AWS_ERROR_SHORT_BUFFER
+
+
+@pytest.mark.parametrize("table_name", ["test", "hpack"])
+def test_stream_lengths_around_chunk_boundaries(contexts, oracle, oracle_tables, table_name):
+    """The fused stream decoder lets its last 1024-bit chunk absorb a tail of fewer than 32 bits: decode
+    streams whose encoded length sits just before / on / just after a chunk boundary, and streams cut at
+    an arbitrary byte (the last code is cut short: what remains is 'padding' or an incomplete code)."""
+    rng = np.random.default_rng(0xC0FFEE)
+    ctx, table = contexts(table_name), oracle_tables[table_name]
+    sampler = refcodec.zipf_symbol_sampler(refcodec.table_arrays(table_name)[1])
+    data = np.ascontiguousarray(sampler[rng.integers(0, 65536, size=400000)])
+    offs = np.array([0, len(data)], dtype=np.uint64)
+    enc = oracle.encode_batch(table, 0xFF, data, offs, 4 * len(data) + 64)
+    stream = enc["out"][:int(enc["out_offsets"][-1])]
+    assert len(stream) > 200000
+    base = (len(stream) // 128 - 3) * 128  # a multiple of the chunk size (128 bytes)
+    for cut in (base - 1, base, base + 1, base + 2, base + 3, base + 4, base + 5, base + 127, 65536, 65537, 131072 + 3):
+        part = np.ascontiguousarray(stream[:cut])
+        o = np.array([0, cut], dtype=np.uint64)
+        want = oracle.decode_batch(table, part, o, len(data) + 64)
+        got = ctx.decode(part, o, len(data) + 64)
+        assert_same_packed(got, want)
+
+
+def test_encode_lengths_around_tile_boundaries(contexts, oracle, oracle_tables):
+    """Items and streams whose sizes straddle the encoder's 8 KiB tiles and 32-symbol thread ranges."""
+    rng = np.random.default_rng(0x71E5)
+    ctx, table = contexts("hpack"), oracle_tables["hpack"]
+    sampler = refcodec.zipf_symbol_sampler(refcodec.table_arrays("hpack")[1])
+    for n in (8191, 8192, 8193, 16384, 16385, 8192 * 3 - 1, 8192 * 5 + 31, 8192 * 5 + 32, 8192 * 5 + 33):
+        data = np.ascontiguousarray(sampler[rng.integers(0, 65536, size=n)])
+        _check_packed_encode_and_roundtrip(ctx, oracle, table, data, np.array([0, n], dtype=np.uint64))
+    # item starts on, just before and just after tile and thread boundaries; runs of empty items between them
+    lens = np.array([8192, 0, 0, 1, 8191, 31, 1, 32, 0, 33, 8192 * 2 - 97, 97, 5, 0, 8192, 8192, 3, 0], dtype=np.int64)
+    offs = np.zeros(len(lens) + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum(lens)
+    data = np.ascontiguousarray(sampler[rng.integers(0, 65536, size=int(offs[-1]))])
+    _check_packed_encode_and_roundtrip(ctx, oracle, table, data, offs)
+
+
+def test_batch_decode_with_oversized_strings(contexts, oracle, oracle_tables):
+    """Tiles of the batch decoder that do not fit its shared-memory stage (a few very long strings among
+    short ones) take the two-pass global-memory route; tiles next to them stay on the fast route."""
+    rng = np.random.default_rng(0xB16)
+    ctx, table = contexts("hpack"), oracle_tables["hpack"]
+    sampler = refcodec.zipf_symbol_sampler(refcodec.table_arrays("hpack")[1])
+    lens = rng.integers(8, 257, size=2000)
+    lens[[5, 700, 701, 1500]] = [40000, 3000, 70000, 2561]
+    offs = np.zeros(len(lens) + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum(lens)
+    data = np.ascontiguousarray(sampler[rng.integers(0, 65536, size=int(offs[-1]))])
+    _check_packed_encode_and_roundtrip(ctx, oracle, table, data, offs)

@@ -1,0 +1,13 @@
+#!/bin/bash
+# Collects the round's ncu evidence on the GPU box into gpurun_out/r1/ (summarised later with tools/ncu_summary.py).
+mkdir -p gpurun_out/r1
+K='hb::|encode_|decode_|stream_|scan_lens|tile_index|fill_packed|rebase|add_base'
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"$K" -c 400 --csv --log-file gpurun_out/r1/launches_hpack_batch.csv \
+    python bench.py --steps 2 --warmup 1 --no-cpu-baseline > /dev/null 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"$K" -c 400 --csv --log-file gpurun_out/r1/launches_stream.csv \
+    python bench.py --steps 2 --warmup 1 --no-cpu-baseline --workload stream > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"encode_tiled|decode_batch" -s 2 -c 2 -o gpurun_out/r1/batch -f \
+    python bench.py --steps 1 --warmup 1 --no-cpu-baseline > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"encode_tiled|stream_fused_kernel" -s 2 -c 2 -o gpurun_out/r1/stream -f \
+    python bench.py --steps 1 --warmup 1 --no-cpu-baseline --workload stream --stream-bytes 268435456 > /dev/null 2>&1
+ls -la gpurun_out/r1
