@@ -1221,6 +1221,23 @@ __global__ void __launch_bounds__(kStreamThreads, 2) stream_fused_kernel(StreamF
             term = r.term;
             last_pos = r.pos;
         }
+        // A chunk that did not enter where its predecessor left is decoded again from there. Inside a warp
+        // that is settled with shuffles right away (no block barrier, the other warps keep decoding); what
+        // is left for the block-wide loop below are the chunks at warp boundaries and the rare cascades.
+        while (true) {
+            const uint32_t prev_exit = __shfl_up_sync(0xffffffffu, exit, 1);
+            const uint32_t prev_term = __shfl_up_sync(0xffffffffu, term, 1);
+            const bool redo = valid && lane > 0 && !exact && prev_term == kTermStop && entry != prev_exit;
+            if (!__any_sync(0xffffffffu, redo)) break;
+            if (redo) {
+                const SpanS r = decode_span_smem<true, true, false>(s_in, s_lut, a.root_bits, s_begin + prev_exit, s_stop, s_end, row_addr);
+                entry = prev_exit;
+                exit = r.term == kTermStop ? r.pos - s_stop : 0u;
+                nsym = r.nsym;
+                term = r.term;
+                last_pos = r.pos;
+            }
+        }
         s_entry[k] = (uint16_t)entry;
         s_exit[k] = (uint16_t)exit;
         s_nsym[k] = nsym;
