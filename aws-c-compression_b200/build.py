@@ -29,7 +29,7 @@ CC = os.environ.get("CC", "gcc")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall",
-]
+] + (["-D" + d for d in os.environ.get("HB_EXTRA_DEFINES", "").split()] if os.environ.get("HB_EXTRA_DEFINES") else [])
 C_FLAGS = ["-std=gnu99", "-O2", "-DNDEBUG", "-fPIC", "-Wall", "-Wextra", "-Wno-unused-parameter"]
 
 C_SOURCES = [

@@ -107,7 +107,8 @@ EXPORTED_SYMBOLS = [
     "aws_huffman_decoder_reset", "aws_huffman_get_encoded_length", "aws_huffman_encode",
     "aws_huffman_decode", "aws_huffman_decoder_allow_growth",
     "huffman_test_transitive", "huffman_test_transitive_chunked",
-    "aws_huffman_batch_ctx_new", "aws_huffman_batch_ctx_destroy", "aws_huffman_encode_batch",
+    "aws_huffman_batch_ctx_new", "aws_huffman_batch_ctx_new_from_code_table", "aws_huffman_batch_ctx_destroy",
+    "aws_huffman_encode_batch",
     "aws_huffman_decode_batch", "aws_huffman_encode_batch_device", "aws_huffman_decode_batch_device",
     "aws_huffman_get_encoded_length_batch", "aws_huffman_batch_ctx_synchronize",
     "aws_huffman_batch_ctx_stream", "aws_huffman_batch_ctx_device", "aws_huffman_batch_ctx_launch_count",
@@ -169,6 +170,8 @@ class Library:
         L, P = self.lib, C.POINTER
         L.aws_huffman_batch_ctx_new.argtypes = [P(C.c_void_p), P(aws_huffman_symbol_coder), C.c_uint8, C.c_int]
         L.aws_huffman_batch_ctx_new.restype = C.c_int
+        L.aws_huffman_batch_ctx_new_from_code_table.argtypes = [P(C.c_void_p), C.c_void_p, C.c_uint8, C.c_int]
+        L.aws_huffman_batch_ctx_new_from_code_table.restype = C.c_int
         L.aws_huffman_batch_ctx_destroy.argtypes = [C.c_void_p]
         L.aws_huffman_batch_ctx_destroy.restype = None
         for name in ("aws_huffman_encode_batch", "aws_huffman_decode_batch"):
@@ -240,6 +243,11 @@ class CodersLibrary:
         fn.restype = C.POINTER(aws_huffman_symbol_coder)
         return fn()
 
+    def code_table_pointer(self, name):
+        fn = getattr(self.lib, name + "_get_code_table")
+        fn.restype = C.POINTER(aws_huffman_code * 256)
+        return fn()
+
     def code_table(self, name):
         fn = getattr(self.lib, name + "_get_code_table")
         fn.restype = C.POINTER(aws_huffman_code * 256)
@@ -267,14 +275,22 @@ def _ptr(x):
 class BatchContext:
     """aws_huffman_batch_ctx for one (coder, eos_padding, device)."""
 
-    def __init__(self, coder, eos_padding=0xFF, device=0, library=None):
+    def __init__(self, coder, eos_padding=0xFF, device=0, library=None, code_table=None):
+        """`coder`: a pointer to aws_huffman_symbol_coder, or None with `code_table` = pointer to 256
+        aws_huffman_code entries (aws_huffman_batch_ctx_new_from_code_table: no callbacks)."""
         self.library = library or product_library()
         self._keep = coder  # callbacks must stay alive while the C side probes them
         handle = C.c_void_p()
-        coder_ptr = coder if not isinstance(coder, aws_huffman_symbol_coder) else C.pointer(coder)
-        rc = self.library.lib.aws_huffman_batch_ctx_new(C.byref(handle), coder_ptr, eos_padding, device)
-        if rc != 0:
-            raise CodecError(self.library.last_error(), "aws_huffman_batch_ctx_new")
+        if code_table is not None:
+            rc = self.library.lib.aws_huffman_batch_ctx_new_from_code_table(
+                C.byref(handle), C.cast(code_table, C.c_void_p), eos_padding, device)
+            if rc != 0:
+                raise CodecError(self.library.last_error(), "aws_huffman_batch_ctx_new_from_code_table")
+        else:
+            coder_ptr = coder if not isinstance(coder, aws_huffman_symbol_coder) else C.pointer(coder)
+            rc = self.library.lib.aws_huffman_batch_ctx_new(C.byref(handle), coder_ptr, eos_padding, device)
+            if rc != 0:
+                raise CodecError(self.library.last_error(), "aws_huffman_batch_ctx_new")
         self.handle = handle
         self.device = device
 

@@ -117,7 +117,6 @@ struct aws_huffman_batch_ctx {
     // pipelined host path: independent lanes (stream + scratch + staging) so that the H2D copy of one
     // sub-batch, the kernels of the next and the D2H copy of the previous one overlap
     hb_host::Lane lanes[hb_host::kLanes];
-    cudaEvent_t offsets_ready = nullptr;
     int sm_count = 148;
     int enc_blocks_per_sm[2] = {0, 0};  // resident blocks per SM of encode_tiled_kernel<seg>
     // staging for the host entry points
@@ -685,6 +684,13 @@ __global__ void encoded_length_kernel(hb::DeviceTables t, const uint8_t *in, con
 
 extern "C" {
 
+static int hb_ctx_from_codes(
+    struct aws_huffman_batch_ctx **out_ctx,
+    const struct aws_huffman_code *codes,
+    struct aws_huffman_symbol_coder *coder, /* optional: its decode callback is cross-checked */
+    uint8_t eos_padding,
+    int device_id);
+
 int aws_huffman_batch_ctx_new(
     struct aws_huffman_batch_ctx **out_ctx,
     struct aws_huffman_symbol_coder *coder,
@@ -693,13 +699,35 @@ int aws_huffman_batch_ctx_new(
 
     if (!out_ctx || !coder || !coder->encode) return aws_raise_error(AWS_ERROR_INVALID_ARGUMENT);
     *out_ctx = nullptr;
-
     // Materialise the coder once over all 256 symbols (host callbacks never run again).
+    struct aws_huffman_code codes[256];
+    for (int s = 0; s < 256; ++s) codes[s] = coder->encode((uint8_t)s, coder->userdata);
+    return hb_ctx_from_codes(out_ctx, codes, coder, eos_padding, device_id);
+}
+
+int aws_huffman_batch_ctx_new_from_code_table(
+    struct aws_huffman_batch_ctx **out_ctx,
+    const struct aws_huffman_code *code_table,
+    uint8_t eos_padding,
+    int device_id) {
+
+    if (!out_ctx || !code_table) return aws_raise_error(AWS_ERROR_INVALID_ARGUMENT);
+    *out_ctx = nullptr;
+    return hb_ctx_from_codes(out_ctx, code_table, nullptr, eos_padding, device_id);
+}
+
+static int hb_ctx_from_codes(
+    struct aws_huffman_batch_ctx **out_ctx,
+    const struct aws_huffman_code *codes,
+    struct aws_huffman_symbol_coder *coder,
+    uint8_t eos_padding,
+    int device_id) {
+
     uint32_t patterns[256];
     uint8_t num_bits[256];
     uint2 enc[256];
     for (int s = 0; s < 256; ++s) {
-        const struct aws_huffman_code c = coder->encode((uint8_t)s, coder->userdata);
+        const struct aws_huffman_code c = codes[s];
         if (c.num_bits > 32) return aws_raise_error(AWS_ERROR_COMPRESSION_INVALID_CODE_TABLE);
         const uint32_t mask = c.num_bits >= 32 ? 0xffffffffu : ((1u << c.num_bits) - 1u);
         patterns[s] = c.pattern & mask;
@@ -713,7 +741,7 @@ int aws_huffman_batch_ctx_new(
 
     // Optional cross-check of the coder's own decode callback on every code (what the reference's
     // huffman_symbol_decoder test does, tests/huffman_test.c:199-220).
-    if (coder->decode) {
+    if (coder && coder->decode) {
         for (int s = 0; s < 256; ++s) {
             if (!num_bits[s]) continue;
             uint8_t sym = 0;
@@ -821,7 +849,6 @@ void aws_huffman_batch_ctx_destroy(struct aws_huffman_batch_ctx *ctx) {
     for (GrowBuf *g : bufs) g->release();
     ctx->scratch.release();
     for (Lane &lane : ctx->lanes) lane.release();
-    if (ctx->offsets_ready) cudaEventDestroy(ctx->offsets_ready);
     (void)cudaGetLastError();
     delete ctx;
 }

@@ -84,6 +84,18 @@ int aws_huffman_batch_ctx_new(
     uint8_t eos_padding,
     int device_id);
 
+/*
+ * The same from a raw 256-entry code table (num_bits == 0: the symbol has no code), e.g. the
+ * <name>_get_code_table() that huffman_generator emits next to <name>_get_coder(): no callback is
+ * ever called (device-ready tables straight from the generator's output).
+ */
+AWS_COMPRESSION_API
+int aws_huffman_batch_ctx_new_from_code_table(
+    struct aws_huffman_batch_ctx **out_ctx,
+    const struct aws_huffman_code *code_table,
+    uint8_t eos_padding,
+    int device_id);
+
 AWS_COMPRESSION_API
 void aws_huffman_batch_ctx_destroy(struct aws_huffman_batch_ctx *ctx);
 

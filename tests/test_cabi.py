@@ -81,6 +81,24 @@ def test_invalid_code_tables_are_rejected_before_touching_the_device(pkg):
         assert err.value.code == pkg.AWS_ERROR_COMPRESSION_INVALID_CODE_TABLE
 
 
+def test_context_from_a_raw_code_table_validates_like_the_callback_route(pkg, coders):
+    """aws_huffman_batch_ctx_new_from_code_table: same checks, no callbacks."""
+    import ctypes as C
+    import torch
+    capi = pkg.capi
+    bad = (capi.aws_huffman_code * 256)()
+    bad[0].pattern, bad[0].num_bits = 0, 1
+    bad[1].pattern, bad[1].num_bits = 0, 1  # two symbols share code '0'
+    with pytest.raises(pkg.CodecError) as err:
+        pkg.BatchContext(None, device=0, code_table=C.pointer(bad))
+    assert err.value.code == pkg.AWS_ERROR_COMPRESSION_INVALID_CODE_TABLE
+    if not torch.cuda.is_available():
+        # a valid table reaches the device step and fails there (no CPU fallback)
+        with pytest.raises(pkg.CodecError) as err:
+            pkg.BatchContext(None, device=0, code_table=coders.code_table_pointer("hpack"))
+        assert err.value.code == pkg.AWS_ERROR_COMPRESSION_DEVICE_FAILURE
+
+
 def test_product_never_references_the_oracle():
     """The product path must not import, link or call anything under oracle/."""
     pkg_dir = os.path.join(ROOT, "aws-c-compression_b200")

@@ -482,3 +482,19 @@ def test_batch_decode_with_oversized_strings(contexts, oracle, oracle_tables):
     offs[1:] = np.cumsum(lens)
     data = np.ascontiguousarray(sampler[rng.integers(0, 65536, size=int(offs[-1]))])
     _check_packed_encode_and_roundtrip(ctx, oracle, table, data, offs)
+
+
+def test_context_from_the_generators_code_table(pkg, coders, oracle, oracle_tables):
+    """A context built from <name>_get_code_table() (no callbacks) encodes and decodes like the one built
+    from <name>_get_coder()."""
+    rng = np.random.default_rng(0x7AB1E)
+    sampler = refcodec.zipf_symbol_sampler(refcodec.table_arrays("hpack")[1])
+    lens = rng.integers(0, 300, size=3000)
+    offs = np.zeros(len(lens) + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum(lens)
+    data = np.ascontiguousarray(sampler[rng.integers(0, 65536, size=int(offs[-1]))])
+    ctx = pkg.BatchContext(None, eos_padding=0xFF, device=0, code_table=coders.code_table_pointer("hpack"))
+    try:
+        _check_packed_encode_and_roundtrip(ctx, oracle, oracle_tables["hpack"], data, offs)
+    finally:
+        ctx.close()
