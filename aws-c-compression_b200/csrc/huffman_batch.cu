@@ -77,7 +77,7 @@ struct Scratch {
     }
 };
 
-constexpr int kLanes = 5;
+constexpr int kLanes = 8;
 struct Lane {
     cudaStream_t stream = nullptr;
     cudaEvent_t kernels_done = nullptr, retired = nullptr;
@@ -450,11 +450,17 @@ int run_host_batch_pipelined(aws_huffman_batch_ctx *ctx, const aws_huffman_batch
 
     const uint32_t max_len = std::max<uint32_t>(1, ctx->tables.max_len);
     const uint32_t min_len = std::max<uint32_t>(1, ctx->tables.min_len);
+    // a sub-batch is retired `depth` issues after it was issued; more lanes than that keep re-use from waiting
+    size_t depth = 2, lanes_used = 5;
+    if (const char *d = getenv("AWS_HUFFMAN_BATCH_PIPE_DEPTH")) depth = std::min<size_t>(6, std::max(1, atoi(d)));
+    if (const char *l = getenv("AWS_HUFFMAN_BATCH_PIPE_LANES")) lanes_used = std::min<size_t>(hb_host::kLanes, std::max(2, atoi(l)));
+    lanes_used = std::max(lanes_used, depth + 2);
+    lanes_used = std::min<size_t>(lanes_used, hb_host::kLanes);
     uint64_t base_out = 0;
     bool overflow = false;
 
     auto issue = [&](size_t j) -> int {
-        Lane &lane = ctx->lanes[j % hb_host::kLanes];
+        Lane &lane = ctx->lanes[j % lanes_used];
         if (lane.in_flight) {
             HB_CUDA_TRY(cudaEventSynchronize(lane.retired));
             lane.in_flight = false;
@@ -509,7 +515,7 @@ int run_host_batch_pipelined(aws_huffman_batch_ctx *ctx, const aws_huffman_batch
     };
 
     auto retire = [&](size_t j) -> int {
-        Lane &lane = ctx->lanes[j % hb_host::kLanes];
+        Lane &lane = ctx->lanes[j % lanes_used];
         const size_t a = begin[j], nj = begin[j + 1] - a;
         HB_CUDA_TRY(cudaEventSynchronize(lane.kernels_done));
         const uint64_t total = *lane.h_total;
@@ -549,7 +555,6 @@ int run_host_batch_pipelined(aws_huffman_batch_ctx *ctx, const aws_huffman_batch
     // A sub-batch is retired (its D2H copies queued) two issues after it was issued; with more lanes than
     // that, re-using a lane never has to wait for a D2H copy that is still running, so uploads of later
     // sub-batches and downloads of earlier ones stay concurrent.
-    const size_t depth = 2;
     static_assert(hb_host::kLanes > 3, "lanes must outnumber the issue-to-retire distance");
     for (size_t j = 0; j < shards + depth; ++j) {
         if (j < shards && issue(j)) return AWS_OP_ERR;
