@@ -2,21 +2,25 @@
 //
 //   decode_batch_kernel        batches of independent short strings (BASELINE configs 2, 5): one thread
 //                              per string, persistent blocks with the whole decode LUT in shared memory.
-//                              Each tile of strings is decoded twice from L1-resident input — a counting
-//                              pass, then (after a block scan and a single-pass decoupled look-back give
-//                              every string its output offset) a writing pass — so the output is packed
-//                              back to back without a separate size query.
+//                              SINGLE PASS: every string is decoded once into a private shared-memory
+//                              row; a block scan and a single-pass decoupled look-back give every string
+//                              its output offset; the rows are moved into a dense shared-memory image of
+//                              the tile's output, which leaves with coalesced 128-bit stores.
 //
-//   stream_*                   one long stream (BASELINE config 4): chunked speculative decode that
-//                              exploits Huffman self-synchronisation. The stream is cut into fixed
+//   stream_fused_kernel        one long stream (BASELINE config 4), SINGLE PASS: chunked speculative decode
+//                              that exploits Huffman self-synchronisation. The stream is cut into fixed
 //                              chunks of kChunkBits; each thread starts kPrerollBits before its chunk at
 //                              an arbitrary bit, and by the time it reaches its chunk it is (almost
-//                              always) on a true code boundary; it then decodes its chunk and records
-//                              where it entered, where it left and how many symbols it saw. A chunk is
-//                              confirmed when it entered exactly where its predecessor left; the few that
-//                              are not are re-decoded from the right spot until the chain is a fixed
-//                              point (correct for ANY prefix code, self-synchronising or not). A scan of
-//                              the symbol counts gives the output offsets and a final pass writes.
+//                              always) on a true code boundary; it then decodes its chunk into its row
+//                              and records where it entered, where it left and how many symbols it saw.
+//                              A chunk is confirmed when it entered exactly where its predecessor left;
+//                              the few that are not are decoded again from the right spot. Output as above.
+//
+//   stream_sync/fix/verify/    the multi-kernel form of the same idea (correct for ANY prefix code,
+//   repair/counts/write        self-synchronising or not): the fallback behind the fused kernel's fail flag.
+//
+//   decode_span_smem           the decode step both single-pass kernels share (register-resident stream
+//                              cursor, branch-free predicated rounds, two symbols per lookup).
 //
 // Termination rules, status, cursor position and leftover register follow the reference loop
 // (source/huffman.c:230-281, refill :196-211); see SURVEY.md App. B.6/B.7 for the closed forms.

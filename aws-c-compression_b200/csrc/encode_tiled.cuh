@@ -1,36 +1,38 @@
 // Tiled, symbol-parallel Huffman encode for the packed layout (BASELINE configs 2, 3, 5).
 //
 // The whole batch is treated as ONE run of input bytes cut into fixed tiles of kEncTile symbols; a
-// block owns a tile regardless of where item boundaries fall, so loads are 128-bit and coalesced
-// and every lane has work. Per tile (three block barriers):
+// block (8 worker warps + 1 scout warp) owns a tile regardless of where item boundaries fall, so loads are
+// 128-bit and coalesced and every lane has work. Per tile:
 //
-//   1. each thread loads 16 symbols (one uint4, prefetched during the previous tile) and looks their
-//      {code, length} up in shared memory ONCE; the 16 pairs stay in registers
+//   1. each worker reads its 32 symbols (fetched with cp.async into shared memory while the previous
+//      tile was packed) and looks their {code, length} up in shared memory ONCE — in a table replicated
+//      so that every lane of a half-warp owns a pair of banks — and keeps the 32 pairs in registers
 //   2. the bit counts are reduced to a "segment function"
 //          p -> p + head                      (no item starts in the range)
 //          p -> ceil8(p + head) + tail        (items start in the range; an item start byte-aligns the
 //                                              output because the previous item is padded, huffman.c:178-184)
 //      and scanned over the block (warp shuffles + one barrier). The tile's own function goes to its
 //      look-back descriptor immediately, so successors rarely wait for it.
-//   3. every thread now knows the tile-relative bit position of its first code and packs its 16 codes
-//      MSB-first with a 64-bit funnel accumulator STRAIGHT INTO THE STAGE at that alignment: whole
-//      words are plain predicated stores, the word a thread shares with its predecessor travels by one
-//      warp shuffle (a segmented OR-scan only when some thread is too short to complete a word) and is
-//      merged by a read-modify-write of the owning thread — no shared-memory atomics, no zeroing.
+//   3. every worker now knows the tile-relative bit position of its first code and packs its codes
+//      MSB-first STRAIGHT INTO THE STAGE at that alignment (enc_append: one multiply-add, one add whose
+//      carry says "a word is complete", one predicated store): whole words are plain stores, the word a
+//      thread shares with its predecessor travels by one warp shuffle (a segmented OR-scan only when some
+//      thread is too short to complete a word) and is merged by a read-modify-write of the owning thread —
+//      no shared-memory atomics, no zeroing.
 //      The stage is tile-relative, in two pieces: the bits before the tile's first item start (whose
 //      output position depends on the tile's absolute bit position G, modulo 8) and everything from
 //      that item start on (byte aligned in the output whatever G is).
-//   4. after the barrier one warp resolves G (single-pass decoupled look-back) — as late as possible,
-//      when the predecessors have long published — while another warp merges the words shared by
-//      neighbouring warps and the rest builds the item-start mask of the next tile
-//   5. both pieces are copied to global memory through one funnel shift per 32-bit word (shift G mod
-//      32 for the first piece, whole bytes for the second), coalesced. The bits that complete the
-//      tile's last byte belong to the next tile's first symbols (or to the EOS padding); one thread
-//      recomputes them from the input, so tiles never write the same byte and no global atomics or
-//      pre-zeroed output are needed.
+//   4. the SCOUT warp resolves G (single-pass decoupled look-back, seg_resolve) while the workers copy
+//      out the previous tile, pack this one and measure the next; it also computes the bits that complete
+//      the tile's last byte
+//   5. one tile later the workers copy both pieces to global memory through one funnel shift per 32-bit
+//      word (shift G mod 32 for the first piece, whole bytes for the second), coalesced. A tile owns the
+//      bytes whose first bit it holds; the bits that complete its last byte belong to the next tile's
+//      first symbols (or to the EOS padding) and are recomputed from the input, so tiles never write the
+//      same byte and no global atomics or pre-zeroed output are needed.
 //
-// Only used when every symbol has a code (no UNKNOWN_SYMBOL possible); otherwise the generic kernel
-// runs. Results are bit-identical to the generic kernel and therefore to the reference.
+// Only used when every symbol has a code of at most 31 bits (no UNKNOWN_SYMBOL possible); otherwise the
+// generic kernel runs. Results are bit-identical to the generic kernel and therefore to the reference.
 #pragma once
 
 #include "device_common.cuh"
