@@ -1137,9 +1137,12 @@ __global__ void __launch_bounds__(kStreamThreads) stream_write_kernel(StreamArgs
 //   2. every thread pre-rolls to find its entry point and decodes its chunk ONCE, emitting the symbols
 //      byte by byte into a private shared-memory row
 //   3. chunks whose entry differs from their predecessor's exit are decoded again from there until the
-//      tile is consistent (block-local; 0.6 % of the chunks on HPACK text). The tile's FIRST chunk cannot
-//      be checked against the previous tile here; it pre-rolls over the whole previous chunk instead and
-//      records (entry, exit of the last chunk) for stream_fused_verify_kernel
+//      tile is consistent (0.6 % of the chunks on HPACK text). The tile's FIRST chunk is checked against
+//      the previous tile: every tile publishes where its last chunk left as soon as it is consistent in
+//      itself (never after waiting for another tile: that would chain the waits through the grid), then
+//      reads its predecessor's record and, if its first chunk entered elsewhere, decodes again from there.
+//      Should that correction ever reach the tile's last chunk (a stream that does not self-synchronise),
+//      the published record was wrong and the `fail` flag goes up
 //   4. block scan of the symbol counts + decoupled look-back -> output offset of the tile
 //   5. rows -> dense image in shared memory (aligned like the global destination) -> 128-bit stores
 // The last chunk of the stream absorbs a tail of fewer than 32 bits, so "the stream ended" can only
@@ -1154,7 +1157,8 @@ struct StreamFusedArgs {
     BatchView b;
     uint64_t *tile_state;    // look-back descriptors, one per tile
     uint32_t *ticket;
-    uint64_t *tile_rec;      // per tile: [15:0] entry of its first chunk, [31:16] exit of its last, [33:32] term of its last
+    uint64_t *tile_rec;      // per tile: [15:0] entry of its first chunk, [31:16] exit of its last, [33:32] term of its
+                             // last, [63] published
     uint32_t *fail;
     uint32_t num_tiles;
     uint32_t row_words;      // row stride in words (odd)
@@ -1212,9 +1216,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) stream_fused_kernel(StreamF
             if (exact) {
                 entry = (uint32_t)(a.begin_bit - begin);
             } else {
-                // the first chunk of a tile cannot be checked in here: it pre-rolls over the whole chunk before it
-                const uint64_t roll = k == 0 ? kChunkBits : kPrerollBits;
-                const uint64_t from = max(begin - roll, a.begin_bit);
+                const uint64_t from = max(begin - kPrerollBits, a.begin_bit);
                 const SpanS pre = decode_span_smem<false, true, true>(
                     s_in, s_lut, a.root_bits, (uint32_t)(from - origin), s_begin, s_end, 0u);
                 entry = pre.pos >= s_begin ? pre.pos - s_begin : 0u;
@@ -1248,34 +1250,60 @@ __global__ void __launch_bounds__(kStreamThreads, 2) stream_fused_kernel(StreamF
         s_term[k] = (uint8_t)term;
         __syncthreads();
 
-        // ---- make the tile consistent ----------------------------------------------------------------------------
-        while (true) {
-            bool redo = false;
-            uint32_t want = 0;
-            if (valid && k > 0 && !exact && s_term[k - 1] == kTermStop && s_entry[k] != s_exit[k - 1]) {
-                redo = true;
-                want = s_exit[k - 1];
+        // ---- make the tile consistent: in itself, then with the previous tile -----------------------------------
+        const uint32_t nvalid = (uint32_t)min((uint64_t)kStreamThreads, a.num_chunks - c0);
+        uint32_t prev_exit0 = 0, prev_term0 = kTermEnd;  // thread 0: where the previous tile's last chunk left
+        uint64_t published = 0;
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            while (true) {
+                bool redo = false;
+                uint32_t want = 0;
+                if (valid && !exact) {
+                    if (k > 0 && s_term[k - 1] == kTermStop && s_entry[k] != s_exit[k - 1]) {
+                        redo = true;
+                        want = s_exit[k - 1];
+                    } else if (k == 0 && pass == 1 && prev_term0 == kTermStop && s_entry[0] != prev_exit0) {
+                        redo = true;
+                        want = prev_exit0;
+                    }
+                }
+                if (!__syncthreads_or(redo)) break;
+                if (redo) {
+                    const SpanS r = decode_span_smem<true, true, false>(s_in, s_lut, a.root_bits, s_begin + want, s_stop, s_end, row_addr);
+                    s_entry[k] = (uint16_t)want;
+                    s_exit[k] = (uint16_t)(r.term == kTermStop ? r.pos - s_stop : 0u);
+                    s_nsym[k] = r.nsym;
+                    s_term[k] = (uint8_t)r.term;
+                    last_pos = r.pos;
+                }
+                __syncthreads();
             }
-            if (!__syncthreads_or(redo)) break;
-            if (redo) {
-                const SpanS r = decode_span_smem<true, true, false>(s_in, s_lut, a.root_bits, s_begin + want, s_stop, s_end, row_addr);
-                s_entry[k] = (uint16_t)want;
-                s_exit[k] = (uint16_t)(r.term == kTermStop ? r.pos - s_stop : 0u);
-                s_nsym[k] = r.nsym;
-                s_term[k] = (uint8_t)r.term;
-                last_pos = r.pos;
+            if (k == 0) {
+                const uint64_t rec = (1ull << 63) | (uint64_t)s_entry[0] | ((uint64_t)s_exit[nvalid - 1] << 16) |
+                                     ((uint64_t)s_term[nvalid - 1] << 32);
+                if (pass == 0) {
+                    // publish first, then look at the predecessor (which did the same: no chain of waits)
+                    published = rec;
+                    st_relaxed_u64(&f.tile_rec[tile], rec);
+                    if (tile > 0 && !exact) {
+                        uint64_t prev;
+                        while (((prev = ld_relaxed_u64(&f.tile_rec[tile - 1])) >> 63) == 0) __nanosleep(100);
+                        prev_exit0 = (uint32_t)(prev >> 16) & 0xffffu;
+                        prev_term0 = (uint32_t)(prev >> 32) & 3u;
+                    }
+                } else if (rec != published) {
+                    st_relaxed_u64(&f.tile_rec[tile], rec);
+                    // the correction reached the last chunk: successors may have used the wrong record
+                    if ((rec >> 16) != (published >> 16)) atomicExch(f.fail, 1u);
+                }
             }
-            __syncthreads();
         }
         if (valid && s_term[k] != kTermStop) atomicMin(&s_first_term, k);
         __syncthreads();
         const uint32_t first_term = s_first_term;
         // something stopped before the stream's last chunk: not for this kernel
         if (first_term < kStreamThreads && c0 + first_term + 1 < a.num_chunks && k == 0) atomicExch(f.fail, 1u);
-        if (k == 0) {
-            const uint32_t nvalid = (uint32_t)min((uint64_t)kStreamThreads, a.num_chunks - c0);
-            f.tile_rec[tile] = (uint64_t)s_entry[0] | ((uint64_t)s_exit[nvalid - 1] << 16) | ((uint64_t)s_term[nvalid - 1] << 32);
-        }
 
         // ---- offsets: block scan + look-back -------------------------------------------------------------------
         const uint32_t cnt = (valid && k <= first_term) ? s_nsym[k] : 0u;
