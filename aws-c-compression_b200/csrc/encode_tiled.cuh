@@ -393,12 +393,19 @@ __device__ __forceinline__ void enc_copy_piece(
 // w-1's leftover into its first word; otherwise (tiny tiles) warp 1 runs a segmented OR-scan over the warps.
 __device__ __forceinline__ void enc_fix_warp_boundaries(
     uint32_t *stage, const uint32_t *s_tail, const uint32_t *s_brk, const uint32_t *s_wpos, uint32_t warp, uint32_t lane) {
+    // s_wpos[w] = stage bit where warp w starts; bit 31 set: the leftover is STORED there instead of ORed in
+    // (encode_slots_kernel: the warp opens piece 1 and the leftover is the last word of piece 0)
     const uint32_t brk = lane < kEncWarps ? s_brk[lane] : 1u;
     const uint32_t endpos = s_wpos[kEncWarps];
     if (__all_sync(0xffffffffu, brk)) {
         if (lane == 0 && warp > 0) {
             const uint32_t cin = s_tail[warp - 1];
-            if (cin) stage[s_wpos[warp] >> 5] |= cin;
+            const uint32_t wp = s_wpos[warp];
+            if (wp & 0x80000000u) {
+                if (wp & 31u) stage[(wp & 0x7fffffffu) >> 5] = cin;  // (stored even when zero: nothing else writes that word)
+            } else if (cin) {
+                stage[wp >> 5] |= cin;
+            }
         }
         if (lane == 1 && warp == kEncWarps - 1 && (endpos & 31u)) stage[endpos >> 5] = s_tail[kEncWarps - 1];
     } else if (warp == 1) {
@@ -407,7 +414,14 @@ __device__ __forceinline__ void enc_fix_warp_boundaries(
         enc_seg_or_scan(v, f, lane);
         uint32_t cin = __shfl_up_sync(0xffffffffu, v, 1);
         if (lane == 0) cin = 0;
-        if (lane < kEncWarps && brk && cin) stage[s_wpos[lane] >> 5] |= cin;  // where warp `lane` starts in the stage
+        if (lane < kEncWarps && brk) {
+            const uint32_t wp = s_wpos[lane];
+            if (wp & 0x80000000u) {
+                if (wp & 31u) stage[(wp & 0x7fffffffu) >> 5] = cin;
+            } else if (cin) {
+                stage[wp >> 5] |= cin;
+            }
+        }
         if (lane == kEncWarps - 1 && (endpos & 31u)) stage[endpos >> 5] = v;
     }
 }

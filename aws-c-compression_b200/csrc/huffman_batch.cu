@@ -10,6 +10,7 @@
 #include "device_common.cuh"
 #include "generic_kernels.cuh"
 #include "encode_tiled.cuh"
+#include "encode_slots.cuh"
 #include "decode_fast.cuh"
 
 #include <algorithm>
@@ -70,9 +71,10 @@ struct GrowBuf {
 };
 // Per-launch kernel scratch (tile descriptors, chunk records, ...). One per concurrent stream.
 struct Scratch {
-    GrowBuf lens, tile_state, tile_first, chunks, chunk_lens, chunk_offsets, fused;
+    GrowBuf lens, tile_state, tile_first, chunks, chunk_lens, chunk_offsets, fused, slot_counts, slot_base;
     void release() {
-        GrowBuf *all[] = {&lens, &tile_state, &tile_first, &chunks, &chunk_lens, &chunk_offsets, &fused};
+        GrowBuf *all[] = {&lens,          &tile_state, &tile_first,  &chunks,   &chunk_lens,
+                          &chunk_offsets, &fused,      &slot_counts, &slot_base};
         for (GrowBuf *g : all) g->release();
     }
 };
@@ -119,6 +121,7 @@ struct aws_huffman_batch_ctx {
     hb_host::Lane lanes[hb_host::kLanes];
     int sm_count = 148;
     int enc_blocks_per_sm[2] = {0, 0};  // resident blocks per SM of encode_tiled_kernel<seg>
+    int enc_slots_blocks_per_sm = 0;
     // staging for the host entry points
     GrowBuf s_in, s_in_off, s_out, s_out_off, s_caps, s_status, s_consumed, s_ovf_pattern, s_ovf_bits, s_left_bits,
         s_left_num;
@@ -169,6 +172,57 @@ int launch_scan(
     scan_lens_kernel<<<(unsigned)tiles, kScanThreads, 0, stream>>>(lens, offsets, n, state, ticket, gate);
     ++ctx->launches;
     HB_CUDA_TRY(cudaGetLastError());
+    return AWS_OP_SUCCESS;
+}
+
+// Packed layout, many items, every symbol has a code: the tiled kernel with item-aligned thread ranges.
+int encode_slots_on_device(
+    aws_huffman_batch_ctx *ctx, Scratch &sc, const hb::BatchView &v, uint64_t total_in, cudaStream_t stream) {
+    const uint64_t num_tiles_ub = (total_in / kEncSymsPerThread + v.n + kSlotsPerTile - 1) / kSlotsPerTile + 1;
+    HB_CUDA_TRY(sc.slot_counts.reserve(v.n * sizeof(uint64_t)));
+    HB_CUDA_TRY(sc.slot_base.reserve((v.n + 1) * sizeof(uint64_t)));
+    HB_CUDA_TRY(sc.tile_first.reserve((num_tiles_ub + 1) * sizeof(EncSlotTile)));
+    slot_count_kernel<<<(unsigned)((v.n + 255) / 256), 256, 0, stream>>>(v.in_offsets, v.n, sc.slot_counts.as<uint64_t>());
+    ++ctx->launches;
+    if (launch_scan(ctx, sc, sc.slot_counts.as<uint64_t>(), sc.slot_base.as<uint64_t>(), v.n, stream)) return AWS_OP_ERR;
+    slot_tile_index_kernel<<<(unsigned)((num_tiles_ub + 1 + 255) / 256), 256, 0, stream>>>(
+        v.in_offsets, sc.slot_base.as<uint64_t>(), v.n, total_in, num_tiles_ub + 1, sc.tile_first.as<EncSlotTile>());
+    ++ctx->launches;
+    const size_t state_bytes = num_tiles_ub * sizeof(uint64_t) + 256;
+    HB_CUDA_TRY(sc.tile_state.reserve(state_bytes));
+    HB_CUDA_TRY(cudaMemsetAsync(sc.tile_state.ptr, 0, state_bytes, stream));
+    EncSlotArgs a{};
+    a.in = v.in;
+    a.in_offsets = v.in_offsets;
+    a.n = v.n;
+    a.total_in = total_in;
+    a.out = v.out;
+    a.out_capacity = v.out_capacity;
+    a.out_offsets = v.out_offsets;
+    a.slot_base = sc.slot_base.as<uint64_t>();
+    a.tiles = sc.tile_first.as<EncSlotTile>();
+    a.tile_state = sc.tile_state.as<uint64_t>();
+    a.ticket = reinterpret_cast<uint32_t *>(a.tile_state + num_tiles_ub);
+    a.num_tiles_ub = (uint32_t)num_tiles_ub;
+    a.eos_padding = ctx->tables.eos_padding;
+    if (!ctx->enc_slots_blocks_per_sm) {
+        int per_sm = 0;
+        HB_CUDA_TRY(cudaFuncSetAttribute(
+            encode_slots_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEncSlotSmemBytes));
+        HB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, encode_slots_kernel, kEncBlock, kEncSlotSmemBytes));
+        ctx->enc_slots_blocks_per_sm = std::max(1, per_sm);
+    }
+    const unsigned grid = (unsigned)std::min<uint64_t>(num_tiles_ub, (uint64_t)ctx->sm_count * ctx->enc_slots_blocks_per_sm);
+    encode_slots_kernel<<<grid, kEncBlock, kEncSlotSmemBytes, stream>>>(ctx->tables.enc, a);
+    ++ctx->launches;
+    HB_CUDA_TRY(cudaGetLastError());
+    if (v.out_lens || v.status || v.consumed || v.overflow_pattern || v.overflow_num_bits) {
+        fill_packed_meta_kernel<<<(unsigned)((v.n + 255) / 256), 256, 0, stream>>>(
+            v.n, v.in_offsets, v.out_offsets, v.out_lens, v.status, v.consumed, v.overflow_pattern,
+            v.overflow_num_bits);
+        ++ctx->launches;
+        HB_CUDA_TRY(cudaGetLastError());
+    }
     return AWS_OP_SUCCESS;
 }
 
@@ -238,6 +292,10 @@ int encode_on_device(
     // (the tiled kernel's multiply-add accumulator needs 1 << len to fit a word: codes of up to 31 bits)
     if (!v.out_caps && !ctx->tables.has_unknown && ctx->tables.max_len <= 31 && total_in > 0 && v.n < 0xffffffffull &&
         (total_in + kEncTile - 1) / kEncTile < 0xffffffffull && !force_generic) {
+        // many items of some length: thread ranges aligned to the items
+        if (v.n > 1 && total_in / v.n >= 24 && total_in < (1ull << 31) && (reinterpret_cast<uintptr_t>(v.in) & 15) == 0 &&
+            !getenv("AWS_HUFFMAN_BATCH_NO_SLOTS"))
+            return encode_slots_on_device(ctx, sc, v, total_in, stream);
         return encode_tiled_on_device(ctx, sc, v, total_in, stream);
     }
     if (!v.out_lens) {
