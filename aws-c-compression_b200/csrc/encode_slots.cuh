@@ -44,12 +44,6 @@ struct EncSlotArgs {
     uint32_t eos_padding;
 };
 
-// counts[i] = slots of item i
-__global__ void slot_count_kernel(const uint64_t *in_offsets, uint64_t n, uint64_t *counts) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) counts[i] = (in_offsets[i + 1] - in_offsets[i] + kEncSymsPerThread - 1) / kEncSymsPerThread;
-}
-
 // Everything the main kernel needs to start on tile j, in one 32-byte record (one load instead of three
 // dependent round trips): the items whose first slot lies in the tile, the tile's first and last input
 // byte, and what is left of the item that continues from the previous tile.

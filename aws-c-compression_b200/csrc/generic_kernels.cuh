@@ -262,7 +262,9 @@ constexpr int kScanTile = kScanThreads * kScanItemsPerThread;
 
 __global__ void __launch_bounds__(kScanThreads)
     scan_lens_kernel(const uint64_t *lens, uint64_t *offsets, uint64_t n, uint64_t *tile_state, uint32_t *ticket,
-                     const uint32_t *gate = nullptr) {
+                     const uint32_t *gate = nullptr, uint32_t slots_of = 0) {
+    // slots_of != 0: `lens` is a CSR offsets array (n + 1 entries) and the values scanned are
+    // ceil((lens[i + 1] - lens[i]) / slots_of), the slot counts of encode_slots_kernel
     if (gate != nullptr && *gate == 0) return;  // (fallback of the fused stream decoder: nothing to redo)
     __shared__ uint32_t s_tile;
     __shared__ uint64_t s_warp_sums[kScanThreads / 32];
@@ -277,7 +279,8 @@ __global__ void __launch_bounds__(kScanThreads)
     uint64_t sum = 0;
 #pragma unroll
     for (int i = 0; i < kScanItemsPerThread; ++i) {
-        v[i] = (first + i < n) ? lens[first + i] : 0;
+        v[i] = 0;
+        if (first + i < n) v[i] = slots_of ? (lens[first + i + 1] - lens[first + i] + slots_of - 1) / slots_of : lens[first + i];
         sum += v[i];
     }
     const uint64_t incl = warp_inclusive_scan64(sum);

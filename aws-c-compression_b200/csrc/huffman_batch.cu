@@ -71,10 +71,10 @@ struct GrowBuf {
 };
 // Per-launch kernel scratch (tile descriptors, chunk records, ...). One per concurrent stream.
 struct Scratch {
-    GrowBuf lens, tile_state, tile_first, chunks, chunk_lens, chunk_offsets, fused, slot_counts, slot_base;
+    GrowBuf lens, tile_state, tile_first, chunks, chunk_lens, chunk_offsets, fused, slot_base;
     void release() {
         GrowBuf *all[] = {&lens,          &tile_state, &tile_first,  &chunks,   &chunk_lens,
-                          &chunk_offsets, &fused,      &slot_counts, &slot_base};
+                          &chunk_offsets, &fused,      &slot_base};
         for (GrowBuf *g : all) g->release();
     }
 };
@@ -162,14 +162,14 @@ hb::BatchView make_view(const aws_huffman_batch *b) {
 // lens -> offsets on the device
 int launch_scan(
     aws_huffman_batch_ctx *ctx, Scratch &sc, const uint64_t *lens, uint64_t *offsets, uint64_t n, cudaStream_t stream,
-    const uint32_t *gate = nullptr) {
+    const uint32_t *gate = nullptr, uint32_t slots_of = 0) {
     const uint64_t tiles = std::max<uint64_t>(1, (n + kScanTile - 1) / kScanTile);
     const size_t state_bytes = tiles * sizeof(uint64_t) + 256;
     HB_CUDA_TRY(sc.tile_state.reserve(state_bytes));
     HB_CUDA_TRY(cudaMemsetAsync(sc.tile_state.ptr, 0, state_bytes, stream));
     uint64_t *state = sc.tile_state.as<uint64_t>();
     uint32_t *ticket = reinterpret_cast<uint32_t *>(state + tiles);
-    scan_lens_kernel<<<(unsigned)tiles, kScanThreads, 0, stream>>>(lens, offsets, n, state, ticket, gate);
+    scan_lens_kernel<<<(unsigned)tiles, kScanThreads, 0, stream>>>(lens, offsets, n, state, ticket, gate, slots_of);
     ++ctx->launches;
     HB_CUDA_TRY(cudaGetLastError());
     return AWS_OP_SUCCESS;
@@ -179,12 +179,10 @@ int launch_scan(
 int encode_slots_on_device(
     aws_huffman_batch_ctx *ctx, Scratch &sc, const hb::BatchView &v, uint64_t total_in, cudaStream_t stream) {
     const uint64_t num_tiles_ub = (total_in / kEncSymsPerThread + v.n + kSlotsPerTile - 1) / kSlotsPerTile + 1;
-    HB_CUDA_TRY(sc.slot_counts.reserve(v.n * sizeof(uint64_t)));
     HB_CUDA_TRY(sc.slot_base.reserve((v.n + 1) * sizeof(uint64_t)));
     HB_CUDA_TRY(sc.tile_first.reserve((num_tiles_ub + 1) * sizeof(EncSlotTile)));
-    slot_count_kernel<<<(unsigned)((v.n + 255) / 256), 256, 0, stream>>>(v.in_offsets, v.n, sc.slot_counts.as<uint64_t>());
-    ++ctx->launches;
-    if (launch_scan(ctx, sc, sc.slot_counts.as<uint64_t>(), sc.slot_base.as<uint64_t>(), v.n, stream)) return AWS_OP_ERR;
+    // slot_base = exclusive scan of the items' slot counts, straight from the offsets
+    if (launch_scan(ctx, sc, v.in_offsets, sc.slot_base.as<uint64_t>(), v.n, stream, nullptr, kEncSymsPerThread)) return AWS_OP_ERR;
     slot_tile_index_kernel<<<(unsigned)((num_tiles_ub + 1 + 255) / 256), 256, 0, stream>>>(
         v.in_offsets, sc.slot_base.as<uint64_t>(), v.n, total_in, num_tiles_ub + 1, sc.tile_first.as<EncSlotTile>());
     ++ctx->launches;
