@@ -160,7 +160,8 @@ class Library:
     """The product library."""
 
     def __init__(self, path=None):
-        path = path or _build.PRODUCT_LIB
+        # AWS_HUFFMAN_B200_LIB: another build of the same library (kernel A/B runs, tools/build_variant.sh)
+        path = path or os.environ.get("AWS_HUFFMAN_B200_LIB") or _build.PRODUCT_LIB
         if not os.path.exists(path):
             raise FileNotFoundError(
                 "%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'`. "

@@ -30,6 +30,14 @@
 
 namespace hb {
 
+#ifndef HB_DEC_UNIFIED
+#define HB_DEC_UNIFIED 1  // 1: links are followed inside the ordinary steps; 0: lanes park and walk once per round
+#endif
+#ifndef HB_DEC_UNIFIED_STEPS
+#define HB_DEC_UNIFIED_STEPS 6
+#endif
+constexpr int kUnifiedSteps = HB_DEC_UNIFIED_STEPS;
+
 constexpr uint32_t kDecLutMaxSmem = 8192;  // entries (32 KiB); larger tables use the generic kernels
 
 // Full lookup of one window (device LUT format: device_common.cuh). Returns a leaf entry or 0 (hole);
@@ -479,6 +487,59 @@ __device__ __forceinline__ SpanS decode_span_smem(
         const uint32_t shift = 32 - root_bits;
         StreamCursor c;
         c.init<kPadded>(in_addr, pos);
+#if HB_DEC_UNIFIED
+        // Every step is ONE table lookup, whatever the table: a lane whose lookup returned a link (a code
+        // longer than the root index: a few % of the symbols) keeps its position and spends its next step
+        // on the sub-table the link names, while the other lanes carry on with their own symbols. No lane
+        // ever waits for another lane's long code and there is no separate walk.
+        //   {tbase, tshift, tused}: table to index, its index shift, window bits the upper levels consumed
+        uint32_t tbase = lut_addr, tshift = shift, tused = 0;
+        while (pos < pair_end) {
+#pragma unroll
+            for (int step = 0; step < kUnifiedSteps; ++step) {
+                const uint32_t e = lds_u32(tbase + (((c.window(pos) << tused) >> tshift) << 2));
+                const bool active = pos < pair_end;
+                const bool leaf = dlut_is_leaf(e);
+                const bool adv = active && leaf;
+                const bool link = active && !leaf && e != 0u;
+                const bool hole = active && e == 0u;
+                // (inactive lanes are always in the root state: a lane only leaves the span on a leaf or a hole)
+                tused = link ? tused + 32u - tshift : 0u;
+                tshift = link ? 32u - (e >> 20) : shift;
+                tbase = link ? lut_addr + ((e & 0xFFFFFu) << 2) : lut_addr;
+                if (adv) pos += e >> 24;
+                if (hole) {
+                    if (kSkipHoles) ++pos;
+                    else pos |= kParked;  // >= 32 real bits and no code matches: UNKNOWN_SYMBOL, the lane stops here
+                }
+                if (kEmit) {
+                    const uint32_t on = adv ? 1u : 0u;
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p st.shared.u8 [%0], %1;\n\t@p st.shared.u8 [%0+1], %2;\n\t}" ::"r"(out_addr),
+                        "r"(e >> 8), "r"(e >> 16), "r"(on)
+                        : "memory");
+                    if (adv) out_addr += e & 3u;
+                }
+                const bool cross = (adv || (kSkipHoles && hole)) && (int)pos >= c.limit;
+                if (cross) {
+                    c.w0 = c.w1;
+                    c.w1 = c.w2;
+                    c.limit += 32;
+                }
+                {
+                    const uint32_t on = cross ? 1u : 0u;
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.shared.u32 %0, [%1];\n\t}"
+                                 : "+r"(c.w2)
+                                 : "r"(c.wa), "r"(on));
+                }
+                if (cross) c.wa += 4;
+            }
+        }
+        if (pos & kParked) {
+            pos &= ~kParked;
+            r.term = kTermUnknown;
+        }
+#else
         while (pos < pair_end) {
             // Straight-line steps: a lane that is parked or past its end runs along with every update
             // predicated off (its lookup reads some valid root entry and is ignored), so the warp never
@@ -534,6 +595,7 @@ __device__ __forceinline__ SpanS decode_span_smem(
                 c.follow(pos);
             }
         }
+#endif
         // the last few symbols of the span: one lookup at a time with the end-of-stream rules (the window is
         // the stream zero-extended, huffman.c:196-211; a code that does not fit ends the stream, :240-255).
         // A two-symbol entry still counts when its second code starts before `stop` and ends inside the stream.
