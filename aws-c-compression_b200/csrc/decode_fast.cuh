@@ -513,11 +513,13 @@ __device__ __forceinline__ SpanS decode_span_smem(
                     else pos |= kParked;  // >= 32 real bits and no code matches: UNKNOWN_SYMBOL, the lane stops here
                 }
                 if (kEmit) {
+#ifndef HB_ABL_NO_EMIT  // (timing-only ablations: HB_ABL_* builds give wrong results on purpose)
                     const uint32_t on = adv ? 1u : 0u;
                     asm volatile(
                         "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p st.shared.u8 [%0], %1;\n\t@p st.shared.u8 [%0+1], %2;\n\t}" ::"r"(out_addr),
                         "r"(e >> 8), "r"(e >> 16), "r"(on)
                         : "memory");
+#endif
                     if (adv) out_addr += e & 3u;
                 }
                 const bool cross = (adv || (kSkipHoles && hole)) && (int)pos >= c.limit;
@@ -656,7 +658,20 @@ struct DecBatchArgs {
     uint32_t *ticket;
     uint32_t num_tiles;
     uint32_t debug;  // AWS_HUFFMAN_BATCH_EXPERIMENT (A/B timing only)
+    uint8_t *scratch;       // deferred output: one slot of scratch_slot bytes per block (16-byte aligned)
+    uint32_t scratch_slot;
 };
+
+// Whole block: the tile whose dense image sits in `slot` goes to its final place, `tile_base` being known now.
+__device__ __forceinline__ void dec_flush_tile(
+    const BatchView &b, const uint8_t *slot, uint64_t tile_base, uint32_t total, uint64_t item0, uint32_t nitems,
+    const uint32_t *s_off_tile) {
+    for (uint32_t it = threadIdx.x; it < nitems; it += blockDim.x) b.out_offsets[item0 + it] = tile_base + s_off_tile[it];
+    if (threadIdx.x == 0 && item0 + nitems == b.n) b.out_offsets[b.n] = tile_base + total;
+    const uint64_t room = tile_base < b.out_capacity ? b.out_capacity - tile_base : 0;
+    const uint32_t ncopy = (uint32_t)min((uint64_t)total, room);
+    block_copy_realign(slot, b.out + tile_base, ncopy, threadIdx.x, blockDim.x);
+}
 
 // Thread-serial copy of n bytes inside shared memory; src is 4-byte aligned, dst is not.
 __device__ __forceinline__ void smem_copy_row(const uint8_t *src, uint8_t *dst, uint32_t n) {
@@ -704,21 +719,27 @@ __global__ void __launch_bounds__(kDecThreads, 2) decode_batch_kernel(DecBatchAr
     __shared__ uint32_t s_start[kDecItemsPerTile];  // first bit of the string in the stage
     __shared__ uint32_t s_bytes[kDecItemsPerTile];  // encoded length
     __shared__ uint32_t s_cnt[kDecItemsPerTile];    // symbols per string
-    __shared__ uint32_t s_off[kDecItemsPerTile];    // exclusive offsets within the tile
+    __shared__ uint32_t s_off[2][kDecItemsPerTile]; // exclusive offsets within the tile (this tile's and the pending one's)
     __shared__ uint32_t s_row[kDecItemsPerTile];    // start of the string's row in the row area
     __shared__ uint16_t s_perm[kDecItemsPerTile];   // strings in order of decreasing length
     static_assert(kDecItemsPerTile <= 2 * kDecThreads, "the block scan handles two strings per thread");
     __shared__ uint32_t s_hist[256];
     __shared__ uint64_t s_warp_sum[kDecWarps];
-    __shared__ uint64_t s_prefix;
-    __shared__ uint32_t s_tile, s_next, s_fits;
+    __shared__ uint64_t s_prefix, s_prefix_now;
+    __shared__ uint32_t s_tile, s_next, s_fits, s_total;
 
     for (uint32_t i = threadIdx.x; i < a.lut_count; i += kDecThreads) s_lut[i] = a.lut[i];
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
     const BatchView &b = a.b;
     const uint32_t rows_addr = (uint32_t)__cvta_generic_to_shared(s_rows);
+    uint8_t *const slot = a.scratch + (size_t)blockIdx.x * a.scratch_slot;  // this block's deferred-output slot
+    // the tile whose image sits in the slot (block-uniform)
+    bool pend = false;
+    uint32_t pend_tile = 0, pend_total = 0, pend_nitems = 0;
+    uint64_t pend_item0 = 0;
 
-    while (true) {
+    uint32_t iter = 0;
+    for (;; ++iter) {
         __syncthreads();  // previous tile fully done (and the LUT is in place on the first trip)
         if (threadIdx.x == 0) {
             s_tile = atomicAdd(a.ticket, 1u);
@@ -840,7 +861,8 @@ __global__ void __launch_bounds__(kDecThreads, 2) decode_batch_kernel(DecBatchAr
         }
         __syncthreads();
 
-        // ---- offsets: block scan (2 strings per thread) + look-back --------------------------------------------
+        // ---- offsets: block scan (2 strings per thread); the tile's count goes out at once ------------------------
+        const uint32_t par = iter & 1u;
         const uint32_t c0 = 2 * threadIdx.x < nitems ? s_cnt[2 * threadIdx.x] : 0u;
         const uint32_t c1 = 2 * threadIdx.x + 1 < nitems ? s_cnt[2 * threadIdx.x + 1] : 0u;
         const uint64_t mine = (uint64_t)c0 + c1;
@@ -852,63 +874,84 @@ __global__ void __launch_bounds__(kDecThreads, 2) decode_batch_kernel(DecBatchAr
             const uint64_t wi = warp_inclusive_scan64(w);
             if (lane < kDecWarps) s_warp_sum[lane] = wi - w;
             const uint64_t total = __shfl_sync(0xffffffffu, wi, kDecWarps - 1);
-            const uint64_t prefix = lookback_exclusive_prefix(a.tile_state, tile, total);
-            if (lane == 0) s_prefix = prefix;
+            if (lane == 0) {
+                lookback_publish_aggregate(a.tile_state, tile, total);
+                s_total = (uint32_t)total;
+            }
         }
         __syncthreads();
-        const uint64_t tile_base = s_prefix;
         {
             const uint64_t e0 = s_warp_sum[warp] + (incl - mine);  // exclusive, within the tile
             if (2 * threadIdx.x < nitems) {
-                s_off[2 * threadIdx.x] = (uint32_t)e0;
-                b.out_offsets[item0 + 2 * threadIdx.x] = tile_base + e0;
+                s_off[par][2 * threadIdx.x] = (uint32_t)e0;
                 if (b.out_lens) b.out_lens[item0 + 2 * threadIdx.x] = c0;
-                if (item0 + 2 * threadIdx.x + 1 == b.n) b.out_offsets[b.n] = tile_base + e0 + c0;
             }
             if (2 * threadIdx.x + 1 < nitems) {
-                s_off[2 * threadIdx.x + 1] = (uint32_t)(e0 + c0);
-                b.out_offsets[item0 + 2 * threadIdx.x + 1] = tile_base + e0 + c0;
+                s_off[par][2 * threadIdx.x + 1] = (uint32_t)(e0 + c0);
                 if (b.out_lens) b.out_lens[item0 + 2 * threadIdx.x + 1] = c1;
-                if (item0 + 2 * threadIdx.x + 2 == b.n) b.out_offsets[b.n] = tile_base + e0 + c0 + c1;
             }
             if (threadIdx.x == 0) s_next = kDecWarps;
-            if (threadIdx.x == kDecThreads - 1) s_hist[0] = (uint32_t)(e0 + c0 + c1);  // symbols in the tile
         }
         __syncthreads();
+        const uint32_t total = s_total;
 
+        // ---- DEFERRED OUTPUT: where a tile's output goes depends on every tile before it. Waiting for that
+        // right here costs 14 % of the kernel (measured: blocks stand still until the slowest predecessor in
+        // flight has counted). So the tile's dense image goes to this block's scratch slot (L2-resident) and
+        // the block moves on; the prefix of the PREVIOUS tile, resolved by warp 0 while the other warps build
+        // this tile's image, is surely there by now, and that tile's bytes and offsets go to their final place.
+        if (warp == 0) {
+            if (pend) {
+                const uint64_t prefix = lookback_resolve(a.tile_state, pend_tile, pend_total);
+                if (lane == 0) s_prefix = prefix;
+            }
+            if (!staged) {  // (two-pass route: needs its own prefix right away)
+                const uint64_t prefix = lookback_resolve(a.tile_state, tile, total);
+                if (lane == 0) s_prefix_now = prefix;
+            }
+        }
         if (staged) {
-            // ---- rows -> dense image (aligned like the global destination) -> global -----------------------------
-            const uint32_t total = s_hist[0];
-            const uint32_t pad = (uint32_t)((reinterpret_cast<uintptr_t>(b.out) + tile_base) & 15);
-            // rows that start before `front` lie where the dense image may grow: they go first (their destination
-            // ends inside the stage area); the host sizes the areas so that the image ends before row offset `front`
+            // rows -> dense image at the front of the stage area. Rows that start before `front` lie where the
+            // image may grow: they go first (their destination ends inside the stage area); the host sizes the
+            // areas so that the image ends before row offset `front`
             const uint32_t front = stage_bytes > kDecMaxRow + 32 ? ((stage_bytes - kDecMaxRow - 32) & ~3u) : 0u;
 #pragma unroll 1
             for (int phase = 0; phase < 2; ++phase) {
                 for (uint32_t it = threadIdx.x; it < nitems; it += kDecThreads) {
                     const uint32_t row = s_row[it];
-                    if ((row < front) == (phase == 0)) smem_copy_row(s_rows + row, s_dense + pad + s_off[it], s_cnt[it]);
+#ifndef HB_ABL_NO_COPY
+                    if ((row < front) == (phase == 0)) smem_copy_row(s_rows + row, s_dense + s_off[par][it], s_cnt[it]);
+#endif
                 }
                 __syncthreads();
             }
-            const uint64_t room = tile_base < b.out_capacity ? b.out_capacity - tile_base : 0;
-            const uint32_t ncopy = (uint32_t)min((uint64_t)total, room);
-            uint8_t *const g0 = b.out + tile_base;
-            const uint32_t head = min(ncopy, (16u - pad) & 15u);
-            const uint32_t nvec = (ncopy - head) >> 4;
-            const uint4 *sv = reinterpret_cast<const uint4 *>(s_dense + pad + head);
-            uint4 *gv = reinterpret_cast<uint4 *>(g0 + head);
+        } else {
+            __syncthreads();
+        }
+        if (pend) {
+            dec_flush_tile(b, slot, s_prefix, pend_total, pend_item0, pend_nitems, s_off[par ^ 1u]);
+            __syncthreads();  // the slot is free again
+        }
+        pend = staged;
+        if (staged) {
+            const uint32_t nvec = (total + 15u) >> 4;
+            const uint4 *sv = reinterpret_cast<const uint4 *>(s_dense);
+            uint4 *gv = reinterpret_cast<uint4 *>(slot);
             for (uint32_t v = threadIdx.x; v < nvec; v += kDecThreads) gv[v] = sv[v];
-            if (threadIdx.x < head) g0[threadIdx.x] = s_dense[pad + threadIdx.x];
-            const uint32_t tail0 = head + 16 * nvec;
-            if (threadIdx.x >= 32 && threadIdx.x - 32 < ncopy - tail0) g0[tail0 + threadIdx.x - 32] = s_dense[pad + tail0 + threadIdx.x - 32];
+            pend_tile = tile;
+            pend_total = total;
+            pend_item0 = item0;
+            pend_nitems = nitems;
         } else {
             // ---- write: decode again from global memory, now storing --------------------------------------------------
+            const uint64_t tile_base = s_prefix_now;
+            for (uint32_t it = threadIdx.x; it < nitems; it += kDecThreads) b.out_offsets[item0 + it] = tile_base + s_off[par][it];
+            if (threadIdx.x == 0 && item0 + nitems == b.n) b.out_offsets[b.n] = tile_base + total;
             for (uint32_t g = warp; g < ngroups;) {
-                const uint32_t slot = g * 32 + lane;
-                if (slot < nitems) {
-                    const uint32_t it = s_perm[slot];
-                    const uint64_t off = tile_base + s_off[it];
+                const uint32_t gslot = g * 32 + lane;
+                if (gslot < nitems) {
+                    const uint32_t it = s_perm[gslot];
+                    const uint64_t off = tile_base + s_off[par][it];
                     const uint64_t room = off < b.out_capacity ? b.out_capacity - off : 0;
                     const uint64_t in0 = b.in_offsets[item0 + it];
                     const uint64_t len = b.in_offsets[item0 + it + 1] - in0;
@@ -922,6 +965,15 @@ __global__ void __launch_bounds__(kDecThreads, 2) decode_batch_kernel(DecBatchAr
                 g = __shfl_sync(0xffffffffu, next, 0);
             }
         }
+    }
+    // the last tile this block decoded is still in its slot
+    if (pend) {
+        if (warp == 0) {
+            const uint64_t prefix = lookback_resolve(a.tile_state, pend_tile, pend_total);
+            if (lane == 0) s_prefix = prefix;
+        }
+        __syncthreads();
+        dec_flush_tile(b, slot, s_prefix, pend_total, pend_item0, pend_nitems, s_off[(iter & 1u) ^ 1u]);
     }
 }
 
@@ -1224,10 +1276,34 @@ struct StreamFusedArgs {
     uint32_t *fail;
     uint32_t num_tiles;
     uint32_t row_words;      // row stride in words (odd)
+    uint8_t *scratch;        // deferred output: one slot of scratch_slot bytes per block (16-byte aligned)
+    uint32_t scratch_slot;
 };
 
 __device__ __forceinline__ uint64_t fused_chunk_stop(const StreamArgs &a, uint64_t k) {
     return k + 1 == a.num_chunks ? a.end_bit : (k + 1) * kChunkBits;
+}
+
+// Whole block: the tile whose dense image sits in `slot` goes to its final place, `tile_base` being known now;
+// the tile of the stream's last chunk also carries the item-level results.
+__device__ __forceinline__ void stream_flush_tile(
+    const StreamFusedArgs &f, const uint8_t *slot, uint64_t tile_base, uint32_t total, bool last_tile, uint32_t last_rel,
+    uint64_t cbits, uint32_t my_term) {
+    const BatchView &b = f.b;
+    const StreamArgs &a = f.s;
+    if (last_tile && threadIdx.x == 0) {
+        const uint64_t nsym = tile_base + last_rel;
+        b.out_offsets[0] = 0;
+        b.out_offsets[1] = nsym;
+        if (b.out_lens) b.out_lens[0] = nsym;
+        if (b.status) b.status[0] = my_term == kTermUnknown ? kStatusUnknownSymbol : kStatusOk;
+        if (b.consumed || b.leftover_working_bits || b.leftover_num_bits)
+            leftover_state(a.in_aligned + (a.begin_bit >> 3), (a.end_bit - a.begin_bit) >> 3, cbits,
+                           my_term == kTermUnknown, b.consumed, b.leftover_working_bits, b.leftover_num_bits);
+    }
+    const uint64_t room = tile_base < b.out_capacity ? b.out_capacity - tile_base : 0;
+    const uint32_t ncopy = (uint32_t)min((uint64_t)total, room);
+    block_copy_realign(slot, b.out + tile_base, ncopy, threadIdx.x, blockDim.x);
 }
 
 __global__ void __launch_bounds__(kStreamThreads, 2) stream_fused_kernel(StreamFusedArgs f) {
@@ -1240,15 +1316,18 @@ __global__ void __launch_bounds__(kStreamThreads, 2) stream_fused_kernel(StreamF
     uint8_t *const s_rows = s_dense + kStageBytes;
     const uint32_t row_bytes = f.row_words * 4;
     __shared__ uint16_t s_entry[kStreamThreads], s_exit[kStreamThreads];
-    __shared__ uint32_t s_nsym[kStreamThreads], s_off[kStreamThreads];
+    __shared__ uint32_t s_nsym[kStreamThreads];
     __shared__ uint8_t s_term[kStreamThreads];
     __shared__ uint32_t s_warp_sum[kStreamThreads / 32];
-    __shared__ uint64_t s_prefix;
-    __shared__ uint32_t s_tile, s_first_term, s_total;
+    __shared__ uint64_t s_prefix, s_last_cbits;
+    __shared__ uint32_t s_tile, s_first_term, s_total, s_last_rel, s_last_term;
 
     for (uint32_t i = threadIdx.x; i < a.lut_count; i += kStreamThreads) s_lut[i] = a.lut[i];
     const uint32_t k = threadIdx.x, lane = lane_id(), warp = threadIdx.x >> 5;
     const uint32_t row_addr = (uint32_t)__cvta_generic_to_shared(s_rows) + k * row_bytes;
+    uint8_t *const slot = f.scratch + (size_t)blockIdx.x * f.scratch_slot;  // this block's deferred-output slot
+    bool pend = false;  // a tile's image sits in the slot (block-uniform)
+    uint32_t pend_tile = 0, pend_total = 0;
 
     while (true) {
         __syncthreads();  // previous tile fully done (and the LUT is in place on the first trip)
@@ -1367,7 +1446,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) stream_fused_kernel(StreamF
         // something stopped before the stream's last chunk: not for this kernel
         if (first_term < kStreamThreads && c0 + first_term + 1 < a.num_chunks && k == 0) atomicExch(f.fail, 1u);
 
-        // ---- offsets: block scan + look-back -------------------------------------------------------------------
+        // ---- offsets: block scan; the tile's count goes out at once ---------------------------------------------
         const uint32_t cnt = (valid && k <= first_term) ? s_nsym[k] : 0u;
         const uint32_t incl = warp_inclusive_scan(cnt);
         if (lane == 31) s_warp_sum[warp] = incl;
@@ -1377,59 +1456,63 @@ __global__ void __launch_bounds__(kStreamThreads, 2) stream_fused_kernel(StreamF
             const uint32_t wi = warp_inclusive_scan(w);
             if (lane < kStreamThreads / 32) s_warp_sum[lane] = wi - w;
             const uint32_t total = __shfl_sync(0xffffffffu, wi, kStreamThreads / 32 - 1);
-            const uint64_t prefix = lookback_exclusive_prefix(f.tile_state, tile, total);
             if (lane == 0) {
-                s_prefix = prefix;
+                lookback_publish_aggregate(f.tile_state, tile, total);
                 s_total = total;
             }
         }
-        __syncthreads();
-        const uint64_t tile_base = s_prefix;
+        __syncthreads();  // everybody is done with the stage
         const uint32_t off = s_warp_sum[warp] + incl - cnt;
-        s_off[k] = off;
+        const uint32_t total = s_total;
 
-        // ---- item-level results (n == 1): the stream's last chunk ----------------------------------------------
+        // ---- item-level results (n == 1) come from the stream's last chunk; they go out with its tile ---------
         if (valid && chunk + 1 == a.num_chunks) {
-            const uint32_t my_term = s_term[k];
-            const uint64_t total = tile_base + off + cnt;
-            const uint64_t cbits = (uint64_t)last_pos + origin - a.begin_bit;  // stream bits turned into symbols
-            const BatchView &b = f.b;
-            b.out_offsets[0] = 0;
-            b.out_offsets[1] = total;
-            if (b.out_lens) b.out_lens[0] = total;
-            if (b.status) b.status[0] = my_term == kTermUnknown ? kStatusUnknownSymbol : kStatusOk;
-            if (b.consumed || b.leftover_working_bits || b.leftover_num_bits)
-                leftover_state(a.in_aligned + (a.begin_bit >> 3), (a.end_bit - a.begin_bit) >> 3, cbits,
-                               my_term == kTermUnknown, b.consumed, b.leftover_working_bits, b.leftover_num_bits);
+            s_last_rel = off + cnt;
+            s_last_cbits = (uint64_t)last_pos + origin - a.begin_bit;  // stream bits turned into symbols
+            s_last_term = s_term[k];
         }
-        __syncthreads();  // s_off complete; everybody is done with the stage
 
-        // ---- rows -> dense image (aligned like the global destination) -> global ----------------------------------
+        // ---- DEFERRED OUTPUT (see decode_batch_kernel): this tile's dense image is parked in the block's scratch
+        // slot; the previous tile, whose prefix warp 0 resolves while the others build the image, goes out now.
+        if (warp == 0 && pend) {
+            const uint64_t prefix = lookback_resolve(f.tile_state, pend_tile, pend_total);
+            if (lane == 0) s_prefix = prefix;
+        }
         {
-            const BatchView &b = f.b;
-            const uint32_t total = s_total;
-            const uint32_t pad = (uint32_t)((reinterpret_cast<uintptr_t>(b.out) + tile_base) & 15);
             // rows that start before `front` lie where the dense image may grow: they go first (their destination
             // ends inside the stage area); the image (<= 256 rows) ends before row offset `front` + stage
             const uint32_t front = kStageBytes - row_bytes - 32;
             const uint32_t row_off = k * row_bytes;
 #pragma unroll 1
             for (int phase = 0; phase < 2; ++phase) {
-                if ((row_off < front) == (phase == 0)) smem_copy_row(s_rows + row_off, s_dense + pad + off, cnt);
+#ifndef HB_ABL_NO_COPY
+                if ((row_off < front) == (phase == 0)) smem_copy_row(s_rows + row_off, s_dense + off, cnt);
+#endif
                 __syncthreads();
             }
-            const uint64_t room = tile_base < b.out_capacity ? b.out_capacity - tile_base : 0;
-            const uint32_t ncopy = (uint32_t)min((uint64_t)total, room);
-            uint8_t *const g0 = b.out + tile_base;
-            const uint32_t head = min(ncopy, (16u - pad) & 15u);
-            const uint32_t nvec = (ncopy - head) >> 4;
-            const uint4 *sv = reinterpret_cast<const uint4 *>(s_dense + pad + head);
-            uint4 *gv = reinterpret_cast<uint4 *>(g0 + head);
-            for (uint32_t v = k; v < nvec; v += kStreamThreads) gv[v] = sv[v];
-            if (k < head) g0[k] = s_dense[pad + k];
-            const uint32_t tail0 = head + 16 * nvec;
-            if (k >= 32 && k - 32 < ncopy - tail0) g0[tail0 + k - 32] = s_dense[pad + tail0 + k - 32];
         }
+        if (pend) {
+            stream_flush_tile(f, slot, s_prefix, pend_total, pend_tile == f.num_tiles - 1, s_last_rel, s_last_cbits, s_last_term);
+            __syncthreads();  // the slot is free again
+        }
+        {
+            const uint32_t nvec = (total + 15u) >> 4;
+            const uint4 *sv = reinterpret_cast<const uint4 *>(s_dense);
+            uint4 *gv = reinterpret_cast<uint4 *>(slot);
+            for (uint32_t v = k; v < nvec; v += kStreamThreads) gv[v] = sv[v];
+        }
+        pend = true;
+        pend_tile = tile;
+        pend_total = total;
+    }
+    // the last tile this block decoded is still in its slot
+    if (pend) {
+        if (warp == 0) {
+            const uint64_t prefix = lookback_resolve(f.tile_state, pend_tile, pend_total);
+            if (lane == 0) s_prefix = prefix;
+        }
+        __syncthreads();
+        stream_flush_tile(f, slot, s_prefix, pend_total, pend_tile == f.num_tiles - 1, s_last_rel, s_last_cbits, s_last_term);
     }
 }
 

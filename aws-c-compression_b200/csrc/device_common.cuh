@@ -141,4 +141,100 @@ __device__ __forceinline__ uint64_t lookback_exclusive_prefix(uint64_t *tile_sta
     return exclusive;
 }
 
+// The same look-back in two halves, for kernels that want slack between them (the single-pass decoders
+// publish a tile's aggregate at once and resolve its prefix ONE TILE LATER, so no block ever stands still
+// waiting for a slower predecessor).
+// One thread, as early as possible:
+__device__ __forceinline__ void lookback_publish_aggregate(uint64_t *tile_state, uint32_t tile, uint64_t aggregate) {
+    const uint64_t flag = tile == 0 ? kLbPrefix : kLbAggregate;
+    st_relaxed_u64(&tile_state[tile], (flag << kLbFlagShift) | (aggregate & kLbValueMask));
+}
+// One full warp, any time later: returns the exclusive prefix of `tile` to every lane and publishes the
+// inclusive one. A round is ONE 256-bit strong load per lane (4 descriptors, 128 per round; strong loads of
+// a warp are served one after the other, see encode_tiled.cuh); lane 0 holds the closest group. A window
+// whose closest descriptors are not published yet is read again as a whole after a short sleep.
+// tile_state must be 32-byte aligned.
+__device__ __forceinline__ uint64_t lookback_resolve(uint64_t *tile_state, uint32_t tile, uint64_t aggregate) {
+    const uint32_t lane = lane_id();
+    if (tile == 0) return 0;
+#ifdef HB_ABL_NO_LOOKBACK  // (timing-only ablation: wrong output positions)
+    return 0;
+#endif
+    uint64_t exclusive = 0;
+    int64_t gtop = ((int64_t)tile - 1) >> 2;  // closest group of four descriptors
+    uint32_t rtop = (tile - 1) & 3;           // last element of that group that is a predecessor
+    while (true) {
+        const int64_t g = gtop - (int64_t)lane;
+        uint64_t word[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) word[e] = kLbPrefix << kLbFlagShift;  // "tile -1": prefix 0
+        if (g >= 0)
+            asm volatile("ld.relaxed.gpu.global.v4.b64 {%0, %1, %2, %3}, [%4];"
+                         : "=l"(word[0]), "=l"(word[1]), "=l"(word[2]), "=l"(word[3])
+                         : "l"(tile_state + 4 * g)
+                         : "memory");
+        const uint32_t last = lane == 0 ? rtop : 3u;
+        // walk my group from the closest element back: sum aggregates up to and including the first prefix
+        uint64_t sum = 0;
+        bool found = false, missing = false;
+#pragma unroll
+        for (int e = 3; e >= 0; --e) {
+            if ((uint32_t)e <= last && !found && !missing) {
+                const uint64_t status = word[e] >> kLbFlagShift;
+                if (status == kLbInvalid) {
+                    missing = true;
+                } else {
+                    sum += word[e] & kLbValueMask;
+                    found = status == kLbPrefix;
+                }
+            }
+        }
+        const uint32_t pmask = __ballot_sync(0xffffffffu, found);
+        const uint32_t first = pmask ? (uint32_t)(__ffs(pmask) - 1) : 32u;
+        if (__any_sync(0xffffffffu, missing && lane <= first)) {
+            __nanosleep(100);
+            continue;
+        }
+        uint64_t contrib = lane <= first ? sum : 0;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
+        exclusive += contrib;
+        if (pmask) break;
+        gtop -= 32;
+        rtop = 3;
+    }
+    if (lane == 0)
+        st_relaxed_u64(&tile_state[tile], (kLbPrefix << kLbFlagShift) | ((exclusive + aggregate) & kLbValueMask));
+    return exclusive;
+}
+
+// Whole block: copies n bytes from `src` (16-byte aligned, with >= 32 readable bytes after n: a block's
+// slot of the deferred-output scratch, read through L2) to `dst` (any alignment) with 128-bit stores.
+__device__ __forceinline__ void block_copy_realign(const uint8_t *src, uint8_t *dst, uint32_t n, uint32_t tid, uint32_t nthreads) {
+    const uint32_t head = min(n, (16u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15)) & 15u);
+    const uint32_t nvec = (n - head) >> 4;
+    const uint4 *sv = reinterpret_cast<const uint4 *>(src);
+    uint4 *dv = reinterpret_cast<uint4 *>(dst + head);
+    const uint32_t tw = head >> 2, r8 = (head & 3u) * 8u;  // the body starts `head` bytes into the image
+    for (uint32_t v = tid; v < nvec; v += nthreads) {
+        const uint4 a = __ldcg(sv + v), b = __ldcg(sv + v + 1);
+        uint32_t w0, w1, w2, w3, w4;
+        switch (tw) {  // (uniform)
+            case 0: w0 = a.x; w1 = a.y; w2 = a.z; w3 = a.w; w4 = b.x; break;
+            case 1: w0 = a.y; w1 = a.z; w2 = a.w; w3 = b.x; w4 = b.y; break;
+            case 2: w0 = a.z; w1 = a.w; w2 = b.x; w3 = b.y; w4 = b.z; break;
+            default: w0 = a.w; w1 = b.x; w2 = b.y; w3 = b.z; w4 = b.w; break;
+        }
+        uint4 o;
+        o.x = __funnelshift_r(w0, w1, r8);
+        o.y = __funnelshift_r(w1, w2, r8);
+        o.z = __funnelshift_r(w2, w3, r8);
+        o.w = __funnelshift_r(w3, w4, r8);
+        dv[v] = o;
+    }
+    if (tid < head) dst[tid] = __ldcg(src + tid);
+    const uint32_t tail0 = head + 16u * nvec;
+    if (tid >= 32 && tid - 32 < n - tail0) dst[tail0 + tid - 32] = __ldcg(src + tail0 + tid - 32);
+}
+
 }  // namespace hb

@@ -71,10 +71,10 @@ struct GrowBuf {
 };
 // Per-launch kernel scratch (tile descriptors, chunk records, ...). One per concurrent stream.
 struct Scratch {
-    GrowBuf lens, tile_state, tile_first, chunks, chunk_lens, chunk_offsets, fused, slot_base;
+    GrowBuf lens, tile_state, tile_first, chunks, chunk_lens, chunk_offsets, fused, slot_base, deferred;
     void release() {
         GrowBuf *all[] = {&lens,          &tile_state, &tile_first,  &chunks,   &chunk_lens,
-                          &chunk_offsets, &fused,      &slot_base};
+                          &chunk_offsets, &fused,      &slot_base,   &deferred};
         for (GrowBuf *g : all) g->release();
     }
 };
@@ -346,6 +346,11 @@ int decode_batch_fast(aws_huffman_batch_ctx *ctx, Scratch &sc, const hb::BatchVi
     const size_t smem = lut_bytes + ((stage_bytes + 15) & ~size_t(15)) + rows_bytes + 64;
     HB_CUDA_TRY(cudaFuncSetAttribute(decode_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned blocks = (unsigned)std::min<uint64_t>(num_tiles, (uint64_t)ctx->sm_count * 2);
+    // deferred output: a block parks the dense image of a tile (never larger than its shared memory) in its own
+    // slot until the next tile is decoded
+    a.scratch_slot = (uint32_t)((smem + 64 + 255) & ~size_t(255));
+    HB_CUDA_TRY(sc.deferred.reserve((size_t)blocks * a.scratch_slot));
+    a.scratch = sc.deferred.as<uint8_t>();
     decode_batch_kernel<<<blocks, kDecThreads, smem, stream>>>(a);
     ++ctx->launches;
     HB_CUDA_TRY(cudaGetLastError());
@@ -405,6 +410,9 @@ int decode_stream_fast(
         a.gate = f.fail;
         HB_CUDA_TRY(cudaFuncSetAttribute(stream_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem));
         const unsigned blocks = (unsigned)std::min<uint64_t>(f.num_tiles, (uint64_t)ctx->sm_count * 2);
+        f.scratch_slot = (uint32_t)((fused_smem + 64 + 255) & ~size_t(255));
+        HB_CUDA_TRY(sc.deferred.reserve((size_t)blocks * f.scratch_slot));
+        f.scratch = sc.deferred.as<uint8_t>();
         stream_fused_kernel<<<blocks, kStreamThreads, fused_smem, stream>>>(f);
         stream_fused_verify_kernel<<<(unsigned)std::min<uint64_t>((f.num_tiles + 255) / 256, 1024), 256, 0, stream>>>(f);
         ctx->launches += 2;

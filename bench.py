@@ -144,7 +144,8 @@ def profiled_traffic(workload, dominant, raw_bytes):
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "r1_kernels.json")))
         group = prof["hpack_batch" if workload == "hpack_batch" else "stream_256MiB"]
-        want = {"encode": "encode_tiled", "decode": "decode_batch" if workload == "hpack_batch" else "stream_fused_kernel"}[dominant]
+        want = {"encode": "encode_slots" if workload == "hpack_batch" else "encode_tiled",
+                "decode": "decode_batch" if workload == "hpack_batch" else "stream_fused_kernel"}[dominant]
         for k in group:
             if want in k["kernel"]:
                 scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
@@ -453,7 +454,8 @@ def main():
             "encode_ms": enc_ms_mean, "decode_ms": dec_ms_mean,
             "raw_bytes_per_gpu": raw_bytes, "encoded_bytes_per_gpu": enc_bytes,
             "roofline": {"bound": "hbm",
-                         "kernel": {"hpack_batch": {"encode": "encode_tiled_kernel<true>", "decode": "decode_batch_kernel"},
+                         "kernel": {"hpack_batch": {"encode": "encode_slots_kernel (+ its slot scan and tile index launches)",
+                                                    "decode": "decode_batch_kernel"},
                                     "stream": {"encode": "encode_tiled_kernel<false>",
                                                "decode": "stream_fused_kernel (+ verify and gated fallback launches)"}}
                                    [args.workload][dominant] + " (per GPU; CUDA events around the " + dominant + " call)",

@@ -6,7 +6,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"$K" -c 400 -
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > /dev/null 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"$K" -c 400 --csv --log-file gpurun_out/r1/launches_stream.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline --workload stream > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"encode_tiled|decode_batch" -s 2 -c 2 -o gpurun_out/r1/batch -f \
+ncu --set full --clock-control none --import-source on -k regex:"encode_slots_kernel|decode_batch" -s 2 -c 2 -o gpurun_out/r1/batch -f \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"encode_tiled|stream_fused_kernel" -s 2 -c 2 -o gpurun_out/r1/stream -f \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline --workload stream --stream-bytes 268435456 > /dev/null 2>&1
