@@ -110,6 +110,8 @@ EXPORTED_SYMBOLS = [
     "aws_huffman_batch_ctx_new", "aws_huffman_batch_ctx_new_from_code_table", "aws_huffman_batch_ctx_destroy",
     "aws_huffman_encode_batch",
     "aws_huffman_decode_batch", "aws_huffman_encode_batch_device", "aws_huffman_decode_batch_device",
+    "aws_huffman_encode_batch_resume", "aws_huffman_decode_batch_resume",
+    "aws_huffman_encode_batch_resume_device", "aws_huffman_decode_batch_resume_device",
     "aws_huffman_get_encoded_length_batch", "aws_huffman_batch_ctx_synchronize",
     "aws_huffman_batch_ctx_stream", "aws_huffman_batch_ctx_device", "aws_huffman_batch_ctx_launch_count",
     "aws_huffman_batch_plan_shards", "aws_huffman_batch_concat_offsets",
@@ -175,10 +177,12 @@ class Library:
         L.aws_huffman_batch_ctx_new_from_code_table.restype = C.c_int
         L.aws_huffman_batch_ctx_destroy.argtypes = [C.c_void_p]
         L.aws_huffman_batch_ctx_destroy.restype = None
-        for name in ("aws_huffman_encode_batch", "aws_huffman_decode_batch"):
+        for name in ("aws_huffman_encode_batch", "aws_huffman_decode_batch",
+                     "aws_huffman_encode_batch_resume", "aws_huffman_decode_batch_resume"):
             getattr(L, name).argtypes = [C.c_void_p, P(aws_huffman_batch)]
             getattr(L, name).restype = C.c_int
-        for name in ("aws_huffman_encode_batch_device", "aws_huffman_decode_batch_device"):
+        for name in ("aws_huffman_encode_batch_device", "aws_huffman_decode_batch_device",
+                     "aws_huffman_encode_batch_resume_device", "aws_huffman_decode_batch_resume_device"):
             getattr(L, name).argtypes = [C.c_void_p, P(aws_huffman_batch), C.c_void_p]
             getattr(L, name).restype = C.c_int
         L.aws_huffman_get_encoded_length_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
@@ -331,7 +335,10 @@ class BatchContext:
             raise CodecError(self.library.last_error(), fn_name)
 
     # ---- host-buffer entry points (numpy in, numpy out) ----
-    def _host(self, encode, data, in_offsets, out_capacity, out_offsets=None, out_caps=None, out=None, extras=True):
+    def _host(self, encode, data, in_offsets, out_capacity, out_offsets=None, out_caps=None, out=None, extras=True,
+              state=None):
+        """state = (overflow_pattern, overflow_num_bits) resp. (leftover_working_bits, leftover_num_bits) of the
+        previous call: the *_resume entry points (the arrays come back updated in the result)."""
         data = np.ascontiguousarray(data, dtype=np.uint8)
         in_offsets = np.ascontiguousarray(in_offsets, dtype=np.uint64)
         n = len(in_offsets) - 1
@@ -352,12 +359,20 @@ class BatchContext:
         else:
             res["leftover_working_bits"] = np.zeros(n, dtype=np.uint64)
             res["leftover_num_bits"] = np.zeros(n, dtype=np.uint8)
+        if state is not None:
+            if encode:
+                res["overflow_pattern"] = np.array(state[0], dtype=np.uint32)
+                res["overflow_num_bits"] = np.array(state[1], dtype=np.uint8)
+            else:
+                res["leftover_working_bits"] = np.array(state[0], dtype=np.uint64)
+                res["leftover_num_bits"] = np.array(state[1], dtype=np.uint8)
         arrays = dict(res)
         arrays["in_"] = data
         arrays["in_offsets"] = in_offsets
         if slotted:
             arrays["out_caps"] = np.ascontiguousarray(out_caps, dtype=np.uint64)
-        self._call("aws_huffman_encode_batch" if encode else "aws_huffman_decode_batch", n, arrays, int(out_capacity))
+        name = "aws_huffman_encode_batch" if encode else "aws_huffman_decode_batch"
+        self._call(name + ("_resume" if state is not None else ""), n, arrays, int(out_capacity))
         return res
 
     def encode(self, data, in_offsets, out_capacity, **kw):

@@ -56,6 +56,9 @@ struct BatchView {
     uint8_t *overflow_num_bits; // encode, optional
     uint64_t *leftover_working_bits;  // decode, optional
     uint8_t *leftover_num_bits;       // decode, optional
+    // *_resume entry points: the encoder's overflow bits / the decoder's bit register of the PREVIOUS call are
+    // read from the state arrays above (which are then required) before the new state is written to them
+    bool resume;
 };
 
 __device__ __forceinline__ uint32_t lane_id() {

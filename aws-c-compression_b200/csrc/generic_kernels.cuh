@@ -65,22 +65,37 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) encode_items_warp_kernel(
     uint32_t carry = 0;      // bits (<8) sitting at the top of stage[0]
     bool stopped = false;
 
+    // Continuing a stream (huffman.c:150-160): the bits the previous call could not place go first, as if
+    // they were the code of a symbol at index -1 (consuming it advances the cursor by nothing).
+    uint32_t in_pattern = 0, in_bits = 0;
+    if (b.resume) {
+        in_bits = b.overflow_num_bits[item];
+        in_pattern = in_bits ? b.overflow_pattern[item] & (0xffffffffu >> (32 - in_bits)) : 0u;
+    }
+
     if (kWrite) {
         for (int w = lane; w < kStageWords; w += 32) stage[w] = 0;
         __syncwarp();
     }
 
-    if (C == 0 && L > 0) {
+    if (C == 0 && (L > 0 || in_bits > 0)) {
         status = kStatusShortBuffer;
         consumed = 0;
         stopped = true;
+        ovf_pattern = in_pattern;  // nothing was written: the pending bits stay pending (:151-153)
+        ovf_bits = in_bits;
     }
 
-    for (uint64_t base = 0; base < L && !stopped; base += 32) {
-        const uint64_t k = base + lane;
-        const bool valid = k < L;
+    // (the step that carries the pending bits runs with base = -32: lane 31 is "symbol -1")
+    for (int64_t base = in_bits ? -32 : 0; base < (int64_t)L && !stopped; base += 32) {
+        const int64_t k = base + (int64_t)lane;
+        const bool pending = k == -1;
+        const bool valid = pending || (k >= 0 && k < (int64_t)L);
         uint32_t code = 0, len = 0;
-        if (valid) {
+        if (pending) {
+            code = in_pattern;
+            len = in_bits;
+        } else if (valid) {
             const uint2 e = s_enc[src[k]];
             code = e.x;
             len = e.y;
@@ -97,10 +112,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) encode_items_warp_kernel(
         if (jj < uu) {
             const uint64_t Bj = __shfl_sync(0xffffffffu, Bk, jj);
             const uint32_t code_j = __shfl_sync(0xffffffffu, code, jj);
-            const bool exact_fit_at_end = (Bj == cap_bits) && (base + jj + 1 == L);
+            const bool exact_fit_at_end = (Bj == cap_bits) && (base + jj + 1 == (int64_t)L);
             if (!exact_fit_at_end) {
                 status = kStatusShortBuffer;
-                consumed = base + jj + 1;
+                consumed = (uint64_t)(base + jj + 1);
                 out_len = C;
                 ovf_bits = (uint32_t)(Bj - cap_bits);
                 ovf_pattern = ovf_bits ? (code_j & (0xffffffffu >> (32 - ovf_bits))) : 0;
@@ -111,7 +126,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) encode_items_warp_kernel(
         } else if (uu < 32) {
             const uint64_t Bprev = __shfl_sync(0xffffffffu, Bk - len, uu);
             status = kStatusUnknownSymbol;
-            consumed = base + uu + 1;
+            consumed = (uint64_t)(base + uu + 1);
             out_len = Bprev >> 3;
             active_lanes = uu;
             clip_bytes = out_len;
@@ -165,10 +180,13 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) encode_items_warp_kernel(
 
     if (lane == 0) {
         b.out_lens[item] = out_len;
-        if (b.status) b.status[item] = status;
-        if (b.consumed) b.consumed[item] = consumed;
-        if (b.overflow_pattern) b.overflow_pattern[item] = ovf_pattern;
-        if (b.overflow_num_bits) b.overflow_num_bits[item] = (uint8_t)ovf_bits;
+        // (packed layout: a measuring launch precedes the writing one; the state arrays are inputs of both)
+        if (kWrite || !b.resume) {
+            if (b.status) b.status[item] = status;
+            if (b.consumed) b.consumed[item] = consumed;
+            if (b.overflow_pattern) b.overflow_pattern[item] = ovf_pattern;
+            if (b.overflow_num_bits) b.overflow_num_bits[item] = (uint8_t)ovf_bits;
+        }
     }
 }
 
@@ -211,7 +229,11 @@ __global__ void __launch_bounds__(256) decode_items_thread_kernel(DeviceTables t
     uint64_t reg = 0;
     uint32_t have = 0;
     uint64_t pos = 0;
-    uint64_t bits_left = len * 8;
+    if (b.resume) {  // decoder->working_bits / num_bits of the previous call (huffman.c:222)
+        have = b.leftover_num_bits[item];
+        reg = have ? b.leftover_working_bits[item] : 0;
+    }
+    uint64_t bits_left = len * 8 + have;
     uint64_t out_len = 0;
     int32_t status = kStatusOk;
 
@@ -245,10 +267,12 @@ __global__ void __launch_bounds__(256) decode_items_thread_kernel(DeviceTables t
     }
 
     b.out_lens[item] = out_len;
-    if (b.status) b.status[item] = status;
-    if (b.consumed) b.consumed[item] = pos;
-    if (b.leftover_working_bits) b.leftover_working_bits[item] = reg;
-    if (b.leftover_num_bits) b.leftover_num_bits[item] = (uint8_t)have;
+    if (kWrite || !b.resume) {
+        if (b.status) b.status[item] = status;
+        if (b.consumed) b.consumed[item] = pos;
+        if (b.leftover_working_bits) b.leftover_working_bits[item] = reg;
+        if (b.leftover_num_bits) b.leftover_num_bits[item] = (uint8_t)have;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

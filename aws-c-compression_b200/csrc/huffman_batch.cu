@@ -288,7 +288,7 @@ int encode_on_device(
     if (v.n == 0) return AWS_OP_SUCCESS;
     const bool force_generic = getenv("AWS_HUFFMAN_BATCH_FORCE_GENERIC") != nullptr;
     // (the tiled kernel's multiply-add accumulator needs 1 << len to fit a word: codes of up to 31 bits)
-    if (!v.out_caps && !ctx->tables.has_unknown && ctx->tables.max_len <= 31 && total_in > 0 && v.n < 0xffffffffull &&
+    if (!v.resume && !v.out_caps && !ctx->tables.has_unknown && ctx->tables.max_len <= 31 && total_in > 0 && v.n < 0xffffffffull &&
         (total_in + kEncTile - 1) / kEncTile < 0xffffffffull && !force_generic) {
         // many items of some length: thread ranges aligned to the items
         if (v.n > 1 && total_in / v.n >= 24 && total_in < (1ull << 31) && (reinterpret_cast<uintptr_t>(v.in) & 15) == 0 &&
@@ -448,7 +448,7 @@ int decode_on_device(
     aws_huffman_batch_ctx *ctx, Scratch &sc, hb::BatchView v, uint64_t total_in, cudaStream_t stream) {
     if (v.n == 0) return AWS_OP_SUCCESS;
     const bool force_generic = getenv("AWS_HUFFMAN_BATCH_FORCE_GENERIC") != nullptr;
-    if (!v.out_caps && ctx->tables.lut_count <= kDecLutMaxSmem && !force_generic) {
+    if (!v.resume && !v.out_caps && ctx->tables.lut_count <= kDecLutMaxSmem && !force_generic) {
         if (v.n == 1 && total_in >= kStreamMinBytes) return decode_stream_fast(ctx, sc, v, total_in, stream);
         return decode_batch_fast(ctx, sc, v, stream);
     }
@@ -634,9 +634,18 @@ int run_host_batch_pipelined(aws_huffman_batch_ctx *ctx, const aws_huffman_batch
 }
 
 // Host-pointer entry point shared by encode and decode: stage in, run, stage out.
-int run_host_batch(aws_huffman_batch_ctx *ctx, const aws_huffman_batch *b, bool encode) {
+int check_resume(const aws_huffman_batch *b, bool encode) {
+    // the state arrays are inputs as well as outputs
+    if (b && b->n &&
+        (encode ? (!b->overflow_pattern || !b->overflow_num_bits) : (!b->leftover_working_bits || !b->leftover_num_bits)))
+        return aws_raise_error(AWS_ERROR_INVALID_ARGUMENT);
+    return AWS_OP_SUCCESS;
+}
+
+int run_host_batch(aws_huffman_batch_ctx *ctx, const aws_huffman_batch *b, bool encode, bool resume = false) {
     if (!ctx) return aws_raise_error(AWS_ERROR_INVALID_ARGUMENT);
     if (check_batch(b)) return AWS_OP_ERR;
+    if (resume && check_resume(b, encode)) return AWS_OP_ERR;
     const size_t n = b->n;
     if (n == 0) {
         if (!b->out_caps && b->out_offsets) b->out_offsets[0] = 0;
@@ -647,7 +656,7 @@ int run_host_batch(aws_huffman_batch_ctx *ctx, const aws_huffman_batch *b, bool 
     const uint64_t total_in = b->in_offsets[n];
     const bool slotted = b->out_caps != nullptr;
     if ((total_in && !b->in) || (b->out_capacity && !b->out)) return aws_raise_error(AWS_ERROR_INVALID_ARGUMENT);
-    if (!slotted && n >= 2 && total_in >= kPipelineMinBytes && !getenv("AWS_HUFFMAN_BATCH_NO_PIPELINE"))
+    if (!resume && !slotted && n >= 2 && total_in >= kPipelineMinBytes && !getenv("AWS_HUFFMAN_BATCH_NO_PIPELINE"))
         return run_host_batch_pipelined(ctx, b, encode);
 
     HB_CUDA_TRY(ctx->s_in.reserve(total_in + 16));
@@ -673,7 +682,18 @@ int run_host_batch(aws_huffman_batch_ctx *ctx, const aws_huffman_batch *b, bool 
             HB_CUDA_TRY(cudaMemcpyAsync(ctx->s_out.ptr, b->out, b->out_capacity, cudaMemcpyHostToDevice, st));
     }
 
+    if (resume) {
+        if (encode) {
+            HB_CUDA_TRY(cudaMemcpyAsync(ctx->s_ovf_pattern.ptr, b->overflow_pattern, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+            HB_CUDA_TRY(cudaMemcpyAsync(ctx->s_ovf_bits.ptr, b->overflow_num_bits, n, cudaMemcpyHostToDevice, st));
+        } else {
+            HB_CUDA_TRY(cudaMemcpyAsync(ctx->s_left_bits.ptr, b->leftover_working_bits, n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+            HB_CUDA_TRY(cudaMemcpyAsync(ctx->s_left_num.ptr, b->leftover_num_bits, n, cudaMemcpyHostToDevice, st));
+        }
+    }
+
     hb::BatchView v{};
+    v.resume = resume;
     v.n = n;
     v.in = ctx->s_in.as<uint8_t>();
     v.in_offsets = ctx->s_in_off.as<uint64_t>();
@@ -928,6 +948,40 @@ int aws_huffman_encode_batch(struct aws_huffman_batch_ctx *ctx, const struct aws
 
 int aws_huffman_decode_batch(struct aws_huffman_batch_ctx *ctx, const struct aws_huffman_batch *batch) {
     return run_host_batch(ctx, batch, false);
+}
+
+int aws_huffman_encode_batch_resume(struct aws_huffman_batch_ctx *ctx, const struct aws_huffman_batch *batch) {
+    return run_host_batch(ctx, batch, true, true);
+}
+
+int aws_huffman_decode_batch_resume(struct aws_huffman_batch_ctx *ctx, const struct aws_huffman_batch *batch) {
+    return run_host_batch(ctx, batch, false, true);
+}
+
+int aws_huffman_encode_batch_resume_device(
+    struct aws_huffman_batch_ctx *ctx,
+    const struct aws_huffman_batch *batch,
+    void *cuda_stream) {
+    if (!ctx) return aws_raise_error(AWS_ERROR_INVALID_ARGUMENT);
+    if (check_batch(batch) || check_resume(batch, true)) return AWS_OP_ERR;
+    HB_CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
+    hb::BatchView v = make_view(batch);
+    v.resume = true;
+    return encode_on_device(ctx, ctx->scratch, v, batch->in_size, st);
+}
+
+int aws_huffman_decode_batch_resume_device(
+    struct aws_huffman_batch_ctx *ctx,
+    const struct aws_huffman_batch *batch,
+    void *cuda_stream) {
+    if (!ctx) return aws_raise_error(AWS_ERROR_INVALID_ARGUMENT);
+    if (check_batch(batch) || check_resume(batch, false)) return AWS_OP_ERR;
+    HB_CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
+    hb::BatchView v = make_view(batch);
+    v.resume = true;
+    return decode_on_device(ctx, ctx->scratch, v, batch->in_size, st);
 }
 
 int aws_huffman_encode_batch_device(

@@ -124,6 +124,39 @@ int aws_huffman_decode_batch_device(
     const struct aws_huffman_batch *batch,
     void *cuda_stream);
 
+/*
+ * Streaming continuation: the batched form of calling aws_huffman_encode /
+ * aws_huffman_decode AGAIN on the same encoder / decoder, the way the reference is fed from network
+ * buffers (tests/huffman_test.c:117-165 and :275-363, source/huffman_testing.c). Per item the state arrays
+ * are read first and written afterwards, and they are required:
+ *     encode: overflow_pattern[i] / overflow_num_bits[i]  = encoder->overflow_bits (source/huffman.c:150-160:
+ *             written before the item's first symbol; left as they are when there is no room at all)
+ *     decode: leftover_working_bits[i] / leftover_num_bits[i] = decoder->working_bits / num_bits
+ *             (source/huffman.c:196-211,222)
+ * Everything else is the contract above. Zeroed state arrays give exactly aws_huffman_encode_batch /
+ * aws_huffman_decode_batch. A caller loops: items that returned AWS_ERROR_SHORT_BUFFER come back with
+ * `in` advanced by consumed[i] and a fresh output slot; a decoder fed chunk by chunk comes back with the
+ * next chunk. These calls run on the per-item kernels (every capacity rule in closed form), not on the
+ * tiled throughput kernels.
+ */
+AWS_COMPRESSION_API
+int aws_huffman_encode_batch_resume(struct aws_huffman_batch_ctx *ctx, const struct aws_huffman_batch *batch);
+
+AWS_COMPRESSION_API
+int aws_huffman_decode_batch_resume(struct aws_huffman_batch_ctx *ctx, const struct aws_huffman_batch *batch);
+
+AWS_COMPRESSION_API
+int aws_huffman_encode_batch_resume_device(
+    struct aws_huffman_batch_ctx *ctx,
+    const struct aws_huffman_batch *batch,
+    void *cuda_stream);
+
+AWS_COMPRESSION_API
+int aws_huffman_decode_batch_resume_device(
+    struct aws_huffman_batch_ctx *ctx,
+    const struct aws_huffman_batch *batch,
+    void *cuda_stream);
+
 /* Batched aws_huffman_get_encoded_length (reference huffman.h:121, huffman.c:107-129):
  * lens[i] = ceil(sum of code lengths / 8), unknown symbols counting 0. Host pointers. */
 AWS_COMPRESSION_API

@@ -11,3 +11,8 @@ ncu --set full --clock-control none --import-source on -k regex:"encode_slots_ke
 ncu --set full --clock-control none --import-source on -k regex:"encode_tiled|stream_fused_kernel" -s 2 -c 2 -o gpurun_out/r1/stream -f \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline --workload stream --stream-bytes 268435456 > /dev/null 2>&1
 ls -la gpurun_out/r1
+# the bench lines of the same build (default arguments)
+python bench.py > gpurun_out/r1/bench_hpack_batch.json 2> gpurun_out/r1/bench_hpack_batch.err
+python bench.py --workload stream > gpurun_out/r1/bench_stream.json 2> gpurun_out/r1/bench_stream.err
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r1/bench_reference.json 2> gpurun_out/r1/bench_reference.err
+tail -c 600 gpurun_out/r1/bench_hpack_batch.json
