@@ -490,6 +490,7 @@ int lane_prepare(Lane &lane) {
     return AWS_OP_SUCCESS;
 }
 
+constexpr uint64_t kZeroCopyMinBytes = 4096;          // pinned payload buffers: kernels work on them in place
 constexpr uint64_t kPipelineMinBytes = 8ull << 20;   // below this one shot is as good
 constexpr uint64_t kPipelineShardBytes = 8ull << 20;  // measured best on PCIe Gen5 x16 (tools/e2e_sweep.sh)
 
@@ -507,6 +508,8 @@ int run_host_batch_pipelined(aws_huffman_batch_ctx *ctx, const aws_huffman_batch
     shards = std::min(shards, n);
     std::vector<size_t> begin(shards + 1);
     if (aws_huffman_batch_plan_shards(b->in_offsets, n, shards, begin.data())) return AWS_OP_ERR;
+    // (cutting the first and last sub-batches smaller, to shorten pipeline fill and drain, was measured: no
+    // effect — 59.5 vs 60.2 GB/s end to end)
     std::vector<uint64_t> shard_base(shards + 1, 0);
 
     for (Lane &lane : ctx->lanes)
@@ -642,6 +645,26 @@ int check_resume(const aws_huffman_batch *b, bool encode) {
     return AWS_OP_SUCCESS;
 }
 
+// The device's alias of [p, p + size) when the range lies in pinned (page-locked, mapped) host memory, else
+// nullptr. Kernels can then read and write the caller's buffers in place over PCIe (zero copy).
+template <typename T>
+T *mapped_alias(T *p, uint64_t size) {
+    if (!p || !size) return nullptr;
+    cudaPointerAttributes first{}, last{};
+    if (cudaPointerGetAttributes(&first, p) != cudaSuccess ||
+        cudaPointerGetAttributes(&last, reinterpret_cast<const uint8_t *>(p) + size - 1) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (first.type != cudaMemoryTypeHost || last.type != cudaMemoryTypeHost || !first.devicePointer || !last.devicePointer)
+        return nullptr;
+    // one allocation: the aliases are as far apart as the host addresses
+    if (reinterpret_cast<const uint8_t *>(last.devicePointer) - reinterpret_cast<const uint8_t *>(first.devicePointer) !=
+        (ptrdiff_t)(size - 1))
+        return nullptr;
+    return reinterpret_cast<T *>(first.devicePointer);
+}
+
 int run_host_batch(aws_huffman_batch_ctx *ctx, const aws_huffman_batch *b, bool encode, bool resume = false) {
     if (!ctx) return aws_raise_error(AWS_ERROR_INVALID_ARGUMENT);
     if (check_batch(b)) return AWS_OP_ERR;
@@ -656,12 +679,30 @@ int run_host_batch(aws_huffman_batch_ctx *ctx, const aws_huffman_batch *b, bool 
     const uint64_t total_in = b->in_offsets[n];
     const bool slotted = b->out_caps != nullptr;
     if ((total_in && !b->in) || (b->out_capacity && !b->out)) return aws_raise_error(AWS_ERROR_INVALID_ARGUMENT);
-    if (!resume && !slotted && n >= 2 && total_in >= kPipelineMinBytes && !getenv("AWS_HUFFMAN_BATCH_NO_PIPELINE"))
+    // ZERO COPY (opt-in: AWS_HUFFMAN_BATCH_ZEROCOPY=1, AWS_HUFFMAN_BATCH_ZC_MODE = 1 input, 2 output, 3 both):
+    // payload buffers in pinned host memory are read and written by the kernels themselves, in place, over
+    // PCIe; only the small per-item arrays are staged. Correct (tests/test_gpu_batch.py::test_zero_copy_host_path)
+    // but MEASURED SLOWER than the copy engines on B200 / PCIe Gen5: kernel-issued reads of host memory run at
+    // 18 GB/s, kernel-issued writes at 48 GB/s, against 55 / 57 GB/s for cudaMemcpyAsync; end to end
+    // 41.8 vs 58.5 GB/s on the 1M-string batch and 26.6 vs 52.1 GB/s on the 1 GiB stream. Kept for callers
+    // with small latency-bound batches and as the measured record of why the host path stages its copies.
+    const uint8_t *zin = nullptr;
+    uint8_t *zout = nullptr;
+    if (!resume && !slotted && total_in >= kZeroCopyMinBytes && getenv("AWS_HUFFMAN_BATCH_ZEROCOPY")) {
+        zin = mapped_alias(b->in, total_in);
+        zout = zin ? mapped_alias(b->out, b->out_capacity) : nullptr;
+    }
+    int zc_mode = 3;
+    if (const char *m = getenv("AWS_HUFFMAN_BATCH_ZC_MODE")) zc_mode = atoi(m);
+    const bool zc_possible = zin && zout;
+    const bool zero_copy_in = zc_possible && (zc_mode & 1), zero_copy_out = zc_possible && (zc_mode & 2);
+    const bool zero_copy = zero_copy_in || zero_copy_out;
+    if (!zero_copy && !resume && !slotted && n >= 2 && total_in >= kPipelineMinBytes && !getenv("AWS_HUFFMAN_BATCH_NO_PIPELINE"))
         return run_host_batch_pipelined(ctx, b, encode);
 
-    HB_CUDA_TRY(ctx->s_in.reserve(total_in + 16));
+    if (!zero_copy_in) HB_CUDA_TRY(ctx->s_in.reserve(total_in + 16));
     HB_CUDA_TRY(ctx->s_in_off.reserve((n + 1) * sizeof(uint64_t)));
-    HB_CUDA_TRY(ctx->s_out.reserve(b->out_capacity + 16));
+    if (!zero_copy_out) HB_CUDA_TRY(ctx->s_out.reserve(b->out_capacity + 16));
     HB_CUDA_TRY(ctx->s_out_off.reserve((n + 1) * sizeof(uint64_t)));
     HB_CUDA_TRY(ctx->scratch.lens.reserve(n * sizeof(uint64_t)));
     if (slotted) HB_CUDA_TRY(ctx->s_caps.reserve(n * sizeof(uint64_t)));
@@ -672,7 +713,7 @@ int run_host_batch(aws_huffman_batch_ctx *ctx, const aws_huffman_batch *b, bool 
     if (!encode && b->leftover_working_bits) HB_CUDA_TRY(ctx->s_left_bits.reserve(n * sizeof(uint64_t)));
     if (!encode && b->leftover_num_bits) HB_CUDA_TRY(ctx->s_left_num.reserve(n));
 
-    if (total_in) HB_CUDA_TRY(cudaMemcpyAsync(ctx->s_in.ptr, b->in, total_in, cudaMemcpyHostToDevice, st));
+    if (total_in && !zero_copy_in) HB_CUDA_TRY(cudaMemcpyAsync(ctx->s_in.ptr, b->in, total_in, cudaMemcpyHostToDevice, st));
     HB_CUDA_TRY(cudaMemcpyAsync(ctx->s_in_off.ptr, b->in_offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     if (slotted) {
         HB_CUDA_TRY(cudaMemcpyAsync(ctx->s_out_off.ptr, b->out_offsets, n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
@@ -695,9 +736,9 @@ int run_host_batch(aws_huffman_batch_ctx *ctx, const aws_huffman_batch *b, bool 
     hb::BatchView v{};
     v.resume = resume;
     v.n = n;
-    v.in = ctx->s_in.as<uint8_t>();
+    v.in = zero_copy_in ? zin : ctx->s_in.as<uint8_t>();
     v.in_offsets = ctx->s_in_off.as<uint64_t>();
-    v.out = ctx->s_out.as<uint8_t>();
+    v.out = zero_copy_out ? zout : ctx->s_out.as<uint8_t>();
     v.out_capacity = b->out_capacity;
     v.out_offsets = ctx->s_out_off.as<uint64_t>();
     v.out_caps = slotted ? ctx->s_caps.as<uint64_t>() : nullptr;
@@ -748,7 +789,7 @@ int run_host_batch(aws_huffman_batch_ctx *ctx, const aws_huffman_batch *b, bool 
     HB_CUDA_TRY(cudaStreamSynchronize(st));
     const uint64_t total_out = b->out_offsets[n];
     if (total_out > b->out_capacity) return aws_raise_error(AWS_ERROR_SHORT_BUFFER);
-    if (total_out) {
+    if (total_out && !zero_copy_out) {
         HB_CUDA_TRY(cudaMemcpyAsync(b->out, v.out, total_out, cudaMemcpyDeviceToHost, st));
         HB_CUDA_TRY(cudaStreamSynchronize(st));
     }

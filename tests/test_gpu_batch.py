@@ -432,6 +432,59 @@ def test_pipelined_host_path(contexts, oracle, oracle_tables, pkg):
     assert err.value.code == pkg.AWS_ERROR_SHORT_BUFFER
 
 
+def _pinned(array):
+    """A page-locked copy of a numpy array (what makes the host entry points work in place, zero copy)."""
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(array)).pin_memory()
+    return t.numpy()
+
+
+@pytest.mark.parametrize("shape", ["batch", "small", "ragged_ends", "stream"])
+def test_zero_copy_host_path(contexts, oracle, oracle_tables, pkg, shape, monkeypatch):
+    """Pinned payload buffers with AWS_HUFFMAN_BATCH_ZEROCOPY=1: the kernels read the input and write the output
+    in the caller's memory over PCIe. Same results as the staged paths, bit for bit; the bytes after the
+    result stay untouched."""
+    monkeypatch.setenv("AWS_HUFFMAN_BATCH_ZEROCOPY", "1")
+    rng = np.random.default_rng({"batch": 1, "small": 2, "ragged_ends": 3, "stream": 4}[shape])
+    ctx, table = contexts("hpack"), oracle_tables["hpack"]
+    if shape == "batch":
+        data, offs = refcodec.random_batch(rng, 120_000, 0, 256, "hpack")
+    elif shape == "small":
+        data, offs = refcodec.random_batch(rng, 700, 0, 40, "hpack")
+    elif shape == "ragged_ends":  # sizes that end right at, or a few bytes off, a 16-byte / page boundary
+        data, offs = refcodec.random_batch(rng, 5000, 1, 100, "hpack")
+        keep = (len(data) // 4096) * 4096 - 3
+        n_keep = int(np.searchsorted(offs, keep, side="right")) - 1
+        offs = offs[:n_keep + 1].copy()
+        data = data[:int(offs[-1])]
+    else:
+        data, offs = refcodec.random_batch(rng, 1, 3_000_001, 3_000_001, "hpack")
+    cap = 2 * len(data) + 64
+    want = oracle.encode_batch(table, 0xFF, data, offs, cap)
+    total = int(want["out_offsets"][-1])
+
+    launches = ctx.launch_count
+    out = _pinned(np.full(cap, 0xA5, dtype=np.uint8))
+    got = ctx.encode(_pinned(data), offs, cap, out=out)
+    assert ctx.launch_count - launches <= 4, "one pass of kernels over the caller's buffers, no sub-batches"
+    assert_same_packed(got, want)
+    assert (got["out"][total:] == 0xA5).all(), "bytes after the result were touched"
+
+    stream = want["out"][:total]
+    want_d = oracle.decode_batch(table, stream, want["out_offsets"], len(data) + 64)
+    out_d = _pinned(np.full(len(data) + 64, 0x5A, dtype=np.uint8))
+    got_d = ctx.decode(_pinned(stream), want["out_offsets"], len(data) + 64, out=out_d)
+    assert_same_packed(got_d, want_d)
+    assert (got_d["out"][len(data):] == 0x5A).all()
+
+    # the call-level SHORT_BUFFER: offsets complete, nothing past the capacity written
+    small = _pinned(np.full(total + 32, 0x77, dtype=np.uint8))
+    with pytest.raises(pkg.CodecError) as err:
+        ctx.encode(_pinned(data), offs, total - 1, out=small)
+    assert err.value.code == pkg.AWS_ERROR_SHORT_BUFFER
+    assert (small[total - 1:] == 0x77).all()
+
+
 @pytest.mark.parametrize("table_name", ["test", "hpack"])
 def test_stream_lengths_around_chunk_boundaries(contexts, oracle, oracle_tables, table_name):
     """The fused stream decoder lets its last 1024-bit chunk absorb a tail of fewer than 32 bits: decode
