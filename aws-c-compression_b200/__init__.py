@@ -12,6 +12,10 @@ from . import build as _build  # noqa: F401
 from .capi import (  # noqa: F401
     AWS_ERROR_COMPRESSION_DEVICE_FAILURE,
     AWS_ERROR_COMPRESSION_INVALID_CODE_TABLE,
+    AWS_ERROR_COMPRESSION_INVALID_PADDING,
+    HPACK_HUFFMAN_ALWAYS,
+    HPACK_HUFFMAN_NEVER,
+    HPACK_HUFFMAN_SMALLEST,
     AWS_ERROR_COMPRESSION_UNKNOWN_SYMBOL,
     AWS_ERROR_SHORT_BUFFER,
     BatchContext,

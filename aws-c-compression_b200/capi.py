@@ -13,6 +13,8 @@ AWS_ERROR_INVALID_ARGUMENT = 34
 AWS_ERROR_COMPRESSION_UNKNOWN_SYMBOL = 3072
 AWS_ERROR_COMPRESSION_DEVICE_FAILURE = 3073
 AWS_ERROR_COMPRESSION_INVALID_CODE_TABLE = 3074
+AWS_ERROR_COMPRESSION_INVALID_PADDING = 3075
+HPACK_HUFFMAN_SMALLEST, HPACK_HUFFMAN_NEVER, HPACK_HUFFMAN_ALWAYS = 0, 1, 2
 
 
 class CodecError(RuntimeError):
@@ -112,6 +114,8 @@ EXPORTED_SYMBOLS = [
     "aws_huffman_decode_batch", "aws_huffman_encode_batch_device", "aws_huffman_decode_batch_device",
     "aws_huffman_encode_batch_resume", "aws_huffman_decode_batch_resume",
     "aws_huffman_encode_batch_resume_device", "aws_huffman_decode_batch_resume_device",
+    "aws_hpack_string_encode_batch", "aws_hpack_string_decode_batch",
+    "aws_hpack_string_encode_batch_device", "aws_hpack_string_decode_batch_device",
     "aws_huffman_get_encoded_length_batch", "aws_huffman_batch_ctx_synchronize",
     "aws_huffman_batch_ctx_stream", "aws_huffman_batch_ctx_device", "aws_huffman_batch_ctx_launch_count",
     "aws_huffman_batch_plan_shards", "aws_huffman_batch_concat_offsets",
@@ -374,6 +378,57 @@ class BatchContext:
         name = "aws_huffman_encode_batch" if encode else "aws_huffman_decode_batch"
         self._call(name + ("_resume" if state is not None else ""), n, arrays, int(out_capacity))
         return res
+
+    # ---- HPACK string literals (hpack_string_batch.h), host buffers ----
+    def hpack_encode_strings(self, data, in_offsets, out_capacity, mode=HPACK_HUFFMAN_SMALLEST):
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        in_offsets = np.ascontiguousarray(in_offsets, dtype=np.uint64)
+        n = len(in_offsets) - 1
+        res = {"out": np.zeros(max(int(out_capacity), 1), dtype=np.uint8), "out_offsets": np.zeros(n + 1, dtype=np.uint64)}
+        fn = self.library.lib.aws_hpack_string_encode_batch
+        fn.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p]
+        fn.restype = C.c_int
+        rc = fn(self.handle, n, data.ctypes.data, in_offsets.ctypes.data, mode, res["out"].ctypes.data, int(out_capacity),
+                res["out_offsets"].ctypes.data)
+        if rc != 0:
+            err = CodecError(self.library.last_error(), "aws_hpack_string_encode_batch")
+            err.result = res
+            raise err
+        return res
+
+    def hpack_decode_strings(self, data, in_offsets, out_capacity):
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        in_offsets = np.ascontiguousarray(in_offsets, dtype=np.uint64)
+        n = len(in_offsets) - 1
+        res = {"out": np.zeros(max(int(out_capacity), 1), dtype=np.uint8), "out_offsets": np.zeros(n + 1, dtype=np.uint64),
+               "status": np.zeros(n, dtype=np.int32)}
+        fn = self.library.lib.aws_hpack_string_decode_batch
+        fn.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+        fn.restype = C.c_int
+        rc = fn(self.handle, n, data.ctypes.data, in_offsets.ctypes.data, res["out"].ctypes.data, int(out_capacity),
+                res["out_offsets"].ctypes.data, res["status"].ctypes.data)
+        if rc != 0:
+            err = CodecError(self.library.last_error(), "aws_hpack_string_decode_batch")
+            err.result = res
+            raise err
+        return res
+
+    def hpack_device(self, encode, n, in_, in_offsets, in_size, out, out_capacity, out_offsets, status=None, mode=0, stream=None):
+        L = self.library.lib
+        if encode:
+            fn = L.aws_hpack_string_encode_batch_device
+            fn.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_uint64,
+                           C.c_void_p, C.c_void_p]
+            rc = fn(self.handle, n, _ptr(in_), _ptr(in_offsets), int(in_size), mode, _ptr(out), int(out_capacity),
+                    _ptr(out_offsets), stream or 0)
+        else:
+            fn = L.aws_hpack_string_decode_batch_device
+            fn.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p,
+                           C.c_void_p, C.c_void_p]
+            rc = fn(self.handle, n, _ptr(in_), _ptr(in_offsets), int(in_size), _ptr(out), int(out_capacity),
+                    _ptr(out_offsets), _ptr(status), stream or 0)
+        if rc != 0:
+            raise CodecError(self.library.last_error(), "aws_hpack_string_%s_batch_device" % ("encode" if encode else "decode"))
 
     def encode(self, data, in_offsets, out_capacity, **kw):
         return self._host(True, data, in_offsets, out_capacity, **kw)

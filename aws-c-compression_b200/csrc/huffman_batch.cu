@@ -5,12 +5,14 @@
 // No CPU fallback lives here: every failure to reach the device surfaces as
 // AWS_ERROR_COMPRESSION_DEVICE_FAILURE.
 #include <aws/compression/huffman_batch.h>
+#include <aws/compression/hpack_string_batch.h>
 
 #include "../host/huffman_lut.h"
 #include "device_common.cuh"
 #include "generic_kernels.cuh"
 #include "encode_tiled.cuh"
 #include "encode_slots.cuh"
+#include "hpack_literals.cuh"
 #include "decode_fast.cuh"
 
 #include <algorithm>
@@ -125,6 +127,10 @@ struct aws_huffman_batch_ctx {
     // staging for the host entry points
     GrowBuf s_in, s_in_off, s_out, s_out_off, s_caps, s_status, s_consumed, s_ovf_pattern, s_ovf_bits, s_left_bits,
         s_left_num;
+    // HPACK string literals (hpack_literals.cuh): packed payloads between the framing and the codec, per-item plans
+    GrowBuf hp_pay, hp_pay_off, hp_dec, hp_dec_off, hp_huff, hp_prefix, hp_lens, hp_pay_lens, hp_dec_status, hp_left_bits,
+        hp_left_num, hp_status;
+    uint64_t *h_scalar = nullptr;  // pinned
 };
 
 namespace {
@@ -796,6 +802,144 @@ int run_host_batch(aws_huffman_batch_ctx *ctx, const aws_huffman_batch *b, bool 
     return AWS_OP_SUCCESS;
 }
 
+// ---------------------------------------------------------------------------------------------
+// HPACK string literals. Device pointers in, device pointers out.
+// ---------------------------------------------------------------------------------------------
+int hpack_encode_on_device(
+    aws_huffman_batch_ctx *ctx, uint64_t n, const uint8_t *raw, const uint64_t *raw_off, uint64_t total_in, uint32_t mode,
+    uint8_t *out, uint64_t out_capacity, uint64_t *out_off, cudaStream_t st) {
+    if (n == 0) return AWS_OP_SUCCESS;
+    const unsigned flat = (unsigned)((n + 255) / 256), warps = (unsigned)((n + 7) / 8);
+    HB_CUDA_TRY(ctx->hp_huff.reserve(n));
+    HB_CUDA_TRY(ctx->hp_lens.reserve(n * sizeof(uint64_t)));
+    const uint8_t *pay = nullptr;
+    const uint64_t *pay_off = nullptr;
+    if (mode != hb::kHpackNever) {
+        const uint64_t cap = total_in * ((std::max<uint32_t>(1, ctx->tables.max_len) + 7) / 8) + 64;
+        HB_CUDA_TRY(ctx->hp_pay.reserve(cap + 64));
+        HB_CUDA_TRY(ctx->hp_pay_off.reserve((n + 1) * sizeof(uint64_t)));
+        hb::BatchView v{};
+        v.n = n;
+        v.in = raw;
+        v.in_offsets = raw_off;
+        v.out = ctx->hp_pay.as<uint8_t>();
+        v.out_capacity = cap;
+        v.out_offsets = ctx->hp_pay_off.as<uint64_t>();
+        if (encode_on_device(ctx, ctx->scratch, v, total_in, st)) return AWS_OP_ERR;
+        pay = ctx->hp_pay.as<uint8_t>();
+        pay_off = ctx->hp_pay_off.as<uint64_t>();
+    }
+    hb::hpack_plan_kernel<<<flat, 256, 0, st>>>(n, raw_off, pay_off, mode, ctx->hp_huff.as<uint8_t>(), ctx->hp_lens.as<uint64_t>());
+    ++ctx->launches;
+    if (launch_scan(ctx, ctx->scratch, ctx->hp_lens.as<uint64_t>(), out_off, n, st)) return AWS_OP_ERR;
+    hb::hpack_frame_kernel<<<warps, 256, 0, st>>>(n, raw, raw_off, pay, pay_off, ctx->hp_huff.as<uint8_t>(), out, out_capacity, out_off);
+    ++ctx->launches;
+    HB_CUDA_TRY(cudaGetLastError());
+    return AWS_OP_SUCCESS;
+}
+
+int hpack_decode_on_device(
+    aws_huffman_batch_ctx *ctx, uint64_t n, const uint8_t *in, const uint64_t *in_off, uint64_t total_in, uint8_t *out,
+    uint64_t out_capacity, uint64_t *out_off, int32_t *status, cudaStream_t st) {
+    if (n == 0) return AWS_OP_SUCCESS;
+    const unsigned flat = (unsigned)((n + 255) / 256), warps = (unsigned)((n + 7) / 8);
+    const uint32_t min_len = std::max<uint32_t>(1, ctx->tables.min_len);
+    const uint64_t dec_cap = total_in * 8 / min_len + 64;
+    HB_CUDA_TRY(ctx->hp_huff.reserve(n));
+    HB_CUDA_TRY(ctx->hp_prefix.reserve(n));
+    HB_CUDA_TRY(ctx->hp_lens.reserve(n * sizeof(uint64_t)));
+    HB_CUDA_TRY(ctx->hp_pay_lens.reserve(n * sizeof(uint64_t)));
+    HB_CUDA_TRY(ctx->hp_pay.reserve(total_in + 64));
+    HB_CUDA_TRY(ctx->hp_pay_off.reserve((n + 1) * sizeof(uint64_t)));
+    HB_CUDA_TRY(ctx->hp_dec.reserve(dec_cap + 64));
+    HB_CUDA_TRY(ctx->hp_dec_off.reserve((n + 1) * sizeof(uint64_t)));
+    HB_CUDA_TRY(ctx->hp_dec_status.reserve(n * sizeof(int32_t)));
+    HB_CUDA_TRY(ctx->hp_left_bits.reserve(n * sizeof(uint64_t)));
+    HB_CUDA_TRY(ctx->hp_left_num.reserve(n));
+    if (!status) {
+        HB_CUDA_TRY(ctx->hp_status.reserve(n * sizeof(int32_t)));
+        status = ctx->hp_status.as<int32_t>();
+    }
+    uint8_t *huff = ctx->hp_huff.as<uint8_t>(), *prefix = ctx->hp_prefix.as<uint8_t>();
+    uint64_t *pay_lens = ctx->hp_pay_lens.as<uint64_t>(), *lens = ctx->hp_lens.as<uint64_t>();
+    uint64_t *pay_off = ctx->hp_pay_off.as<uint64_t>(), *dec_off = ctx->hp_dec_off.as<uint64_t>();
+
+    // 1. parse the literals; 2. the Huffman payloads, packed
+    hb::hpack_parse_kernel<<<flat, 256, 0, st>>>(n, in, in_off, huff, prefix, pay_lens, lens, status);
+    ++ctx->launches;
+    if (launch_scan(ctx, ctx->scratch, lens, pay_off, n, st)) return AWS_OP_ERR;
+    hb::hpack_move_kernel<<<warps, 256, 0, st>>>(
+        n, in, in_off, prefix, pay_lens, nullptr, nullptr, huff, false, true, status, ctx->hp_pay.as<uint8_t>(), total_in, pay_off);
+    ++ctx->launches;
+    // 3. decode them (the single-stream kernels size themselves from the payload length: needed on the host for n == 1)
+    uint64_t pay_total = total_in;
+    if (n == 1) {
+        if (!ctx->h_scalar) HB_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_scalar), sizeof(uint64_t), cudaHostAllocDefault));
+        HB_CUDA_TRY(cudaMemcpyAsync(ctx->h_scalar, pay_off + 1, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        HB_CUDA_TRY(cudaStreamSynchronize(st));
+        pay_total = *ctx->h_scalar;
+    }
+    hb::BatchView v{};
+    v.n = n;
+    v.in = ctx->hp_pay.as<uint8_t>();
+    v.in_offsets = pay_off;
+    v.out = ctx->hp_dec.as<uint8_t>();
+    v.out_capacity = dec_cap;
+    v.out_offsets = dec_off;
+    v.status = ctx->hp_dec_status.as<int32_t>();
+    v.leftover_working_bits = ctx->hp_left_bits.as<uint64_t>();
+    v.leftover_num_bits = ctx->hp_left_num.as<uint8_t>();
+    if (decode_on_device(ctx, ctx->scratch, v, pay_total, st)) return AWS_OP_ERR;
+    // 4. padding rule, final lengths; 5. the strings, packed
+    hb::hpack_finish_kernel<<<flat, 256, 0, st>>>(
+        n, huff, pay_lens, dec_off, v.status, v.leftover_working_bits, v.leftover_num_bits, status, lens);
+    ++ctx->launches;
+    if (launch_scan(ctx, ctx->scratch, lens, out_off, n, st)) return AWS_OP_ERR;
+    hb::hpack_move_kernel<<<warps, 256, 0, st>>>(
+        n, in, in_off, prefix, pay_lens, ctx->hp_dec.as<uint8_t>(), dec_off, huff, true, false, status, out, out_capacity, out_off);
+    ++ctx->launches;
+    HB_CUDA_TRY(cudaGetLastError());
+    return AWS_OP_SUCCESS;
+}
+
+// Host pointers: stage in, run, stage out.
+int hpack_run_host(
+    aws_huffman_batch_ctx *ctx, bool encode, size_t n, const uint8_t *in, const uint64_t *in_off, uint32_t mode, uint8_t *out,
+    uint64_t out_capacity, uint64_t *out_off, int32_t *status) {
+    if (!ctx || (n && (!in_off || !out_off))) return aws_raise_error(AWS_ERROR_INVALID_ARGUMENT);
+    if (n == 0) {
+        if (out_off) out_off[0] = 0;
+        return AWS_OP_SUCCESS;
+    }
+    const uint64_t total_in = in_off[n];
+    if ((total_in && !in) || (out_capacity && !out)) return aws_raise_error(AWS_ERROR_INVALID_ARGUMENT);
+    HB_CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    HB_CUDA_TRY(ctx->s_in.reserve(total_in + 16));
+    HB_CUDA_TRY(ctx->s_in_off.reserve((n + 1) * sizeof(uint64_t)));
+    HB_CUDA_TRY(ctx->s_out.reserve(out_capacity + 16));
+    HB_CUDA_TRY(ctx->s_out_off.reserve((n + 1) * sizeof(uint64_t)));
+    HB_CUDA_TRY(ctx->s_status.reserve(n * sizeof(int32_t)));
+    if (total_in) HB_CUDA_TRY(cudaMemcpyAsync(ctx->s_in.ptr, in, total_in, cudaMemcpyHostToDevice, st));
+    HB_CUDA_TRY(cudaMemcpyAsync(ctx->s_in_off.ptr, in_off, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    const int rc = encode ? hpack_encode_on_device(ctx, n, ctx->s_in.as<uint8_t>(), ctx->s_in_off.as<uint64_t>(), total_in, mode,
+                                                   ctx->s_out.as<uint8_t>(), out_capacity, ctx->s_out_off.as<uint64_t>(), st)
+                          : hpack_decode_on_device(ctx, n, ctx->s_in.as<uint8_t>(), ctx->s_in_off.as<uint64_t>(), total_in,
+                                                   ctx->s_out.as<uint8_t>(), out_capacity, ctx->s_out_off.as<uint64_t>(),
+                                                   ctx->s_status.as<int32_t>(), st);
+    if (rc) return AWS_OP_ERR;
+    HB_CUDA_TRY(cudaMemcpyAsync(out_off, ctx->s_out_off.ptr, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    if (!encode && status) HB_CUDA_TRY(cudaMemcpyAsync(status, ctx->s_status.ptr, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    HB_CUDA_TRY(cudaStreamSynchronize(st));
+    const uint64_t total_out = out_off[n];
+    if (total_out > out_capacity) return aws_raise_error(AWS_ERROR_SHORT_BUFFER);
+    if (total_out) {
+        HB_CUDA_TRY(cudaMemcpyAsync(out, ctx->s_out.ptr, total_out, cudaMemcpyDeviceToHost, st));
+        HB_CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    return AWS_OP_SUCCESS;
+}
+
 __global__ void encoded_length_kernel(hb::DeviceTables t, const uint8_t *in, const uint64_t *in_offsets, uint64_t n, uint64_t *lens) {
     __shared__ uint32_t s_len[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_len[i] = t.enc[i].y;
@@ -975,8 +1119,12 @@ void aws_huffman_batch_ctx_destroy(struct aws_huffman_batch_ctx *ctx) {
     if (ctx->d_lut) cudaFree(ctx->d_lut);
     GrowBuf *bufs[] = {&ctx->s_in,       &ctx->s_in_off,      &ctx->s_out,      &ctx->s_out_off,
                        &ctx->s_caps,     &ctx->s_status,      &ctx->s_consumed, &ctx->s_ovf_pattern,
-                       &ctx->s_ovf_bits, &ctx->s_left_bits,   &ctx->s_left_num};
+                       &ctx->s_ovf_bits, &ctx->s_left_bits,   &ctx->s_left_num, &ctx->hp_pay,
+                       &ctx->hp_pay_off, &ctx->hp_dec,        &ctx->hp_dec_off, &ctx->hp_huff,
+                       &ctx->hp_prefix,  &ctx->hp_lens,       &ctx->hp_pay_lens, &ctx->hp_dec_status,
+                       &ctx->hp_left_bits, &ctx->hp_left_num, &ctx->hp_status};
     for (GrowBuf *g : bufs) g->release();
+    if (ctx->h_scalar) cudaFreeHost(ctx->h_scalar);
     ctx->scratch.release();
     for (Lane &lane : ctx->lanes) lane.release();
     (void)cudaGetLastError();
@@ -1045,6 +1193,38 @@ int aws_huffman_decode_batch_device(
     HB_CUDA_TRY(cudaSetDevice(ctx->device));
     cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
     return decode_on_device(ctx, ctx->scratch, make_view(batch), batch->in_size, st);
+}
+
+int aws_hpack_string_encode_batch(
+    struct aws_huffman_batch_ctx *ctx, size_t n, const uint8_t *in, const uint64_t *in_offsets,
+    enum aws_hpack_huffman_mode mode, uint8_t *out, uint64_t out_capacity, uint64_t *out_offsets) {
+    if ((unsigned)mode > (unsigned)AWS_HPACK_HUFFMAN_ALWAYS) return aws_raise_error(AWS_ERROR_INVALID_ARGUMENT);
+    return hpack_run_host(ctx, true, n, in, in_offsets, (uint32_t)mode, out, out_capacity, out_offsets, nullptr);
+}
+
+int aws_hpack_string_decode_batch(
+    struct aws_huffman_batch_ctx *ctx, size_t n, const uint8_t *in, const uint64_t *in_offsets, uint8_t *out,
+    uint64_t out_capacity, uint64_t *out_offsets, int32_t *status) {
+    return hpack_run_host(ctx, false, n, in, in_offsets, 0, out, out_capacity, out_offsets, status);
+}
+
+int aws_hpack_string_encode_batch_device(
+    struct aws_huffman_batch_ctx *ctx, size_t n, const uint8_t *in, const uint64_t *in_offsets, uint64_t in_size,
+    enum aws_hpack_huffman_mode mode, uint8_t *out, uint64_t out_capacity, uint64_t *out_offsets, void *cuda_stream) {
+    if (!ctx || (n && (!in_offsets || !out_offsets)) || (unsigned)mode > (unsigned)AWS_HPACK_HUFFMAN_ALWAYS)
+        return aws_raise_error(AWS_ERROR_INVALID_ARGUMENT);
+    HB_CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
+    return hpack_encode_on_device(ctx, n, in, in_offsets, in_size, (uint32_t)mode, out, out_capacity, out_offsets, st);
+}
+
+int aws_hpack_string_decode_batch_device(
+    struct aws_huffman_batch_ctx *ctx, size_t n, const uint8_t *in, const uint64_t *in_offsets, uint64_t in_size,
+    uint8_t *out, uint64_t out_capacity, uint64_t *out_offsets, int32_t *status, void *cuda_stream) {
+    if (!ctx || (n && (!in_offsets || !out_offsets))) return aws_raise_error(AWS_ERROR_INVALID_ARGUMENT);
+    HB_CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
+    return hpack_decode_on_device(ctx, n, in, in_offsets, in_size, out, out_capacity, out_offsets, status, st);
 }
 
 int aws_huffman_get_encoded_length_batch(

@@ -20,6 +20,10 @@ static struct aws_error_info s_error_table[] = {
         AWS_ERROR_COMPRESSION_INVALID_CODE_TABLE,
         "The symbol coder does not describe a prefix code of at most 32 bits.",
         "aws-c-compression"),
+    [COMPRESSION_ERROR_SLOT(AWS_ERROR_COMPRESSION_INVALID_PADDING)] = AWS_DEFINE_ERROR_INFO(
+        AWS_ERROR_COMPRESSION_INVALID_PADDING,
+        "A Huffman-coded HPACK string literal ends in invalid padding (RFC 7541 section 5.2).",
+        "aws-c-compression"),
 };
 
 static struct aws_error_info_list s_error_info = {

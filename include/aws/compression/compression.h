@@ -25,6 +25,10 @@ enum aws_compression_error {
      * code (two codes collide, or a code is longer than 32 bits). */
     AWS_ERROR_COMPRESSION_INVALID_CODE_TABLE,
 
+    /* New in the B200 build (hpack_string_batch.h): a Huffman-coded HPACK string literal whose padding is
+     * a byte or longer, is not all ones, or contains the EOS symbol (RFC 7541 section 5.2). */
+    AWS_ERROR_COMPRESSION_INVALID_PADDING,
+
     AWS_ERROR_END_COMPRESSION_RANGE = AWS_ERROR_ENUM_END_RANGE(AWS_C_COMPRESSION_PACKAGE_ID)
 };
 
