@@ -657,6 +657,8 @@ struct DecBatchArgs {
     uint64_t *tile_state;
     uint32_t *ticket;
     uint32_t num_tiles;
+    uint32_t items_per_tile;  // <= kDecItemsPerTile, a multiple of 32: fewer when the strings are long, so that a
+                              // tile of average strings still fits the stage
     uint32_t debug;  // AWS_HUFFMAN_BATCH_EXPERIMENT (A/B timing only)
     uint8_t *scratch;       // deferred output: one slot of scratch_slot bytes per block (16-byte aligned)
     uint32_t scratch_slot;
@@ -750,8 +752,8 @@ __global__ void __launch_bounds__(kDecThreads, 2) decode_batch_kernel(DecBatchAr
         __syncthreads();
         const uint32_t tile = s_tile;
         if (tile >= a.num_tiles) break;
-        const uint64_t item0 = (uint64_t)tile * kDecItemsPerTile;
-        const uint32_t nitems = (uint32_t)min((uint64_t)kDecItemsPerTile, b.n - item0);
+        const uint64_t item0 = (uint64_t)tile * a.items_per_tile;
+        const uint32_t nitems = (uint32_t)min((uint64_t)a.items_per_tile, b.n - item0);
         const uint32_t ngroups = (nitems + 31) / 32;
 
         // ---- string table: where each string starts in the stage and in the row area; length histogram -------

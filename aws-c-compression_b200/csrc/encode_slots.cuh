@@ -20,7 +20,6 @@
 #pragma once
 
 #include "encode_tiled.cuh"
-#include <cstdio>
 
 namespace hb {
 
@@ -416,9 +415,6 @@ __global__ void __launch_bounds__(kEncBlock, 2) encode_slots_kernel(const uint2 
                 enc_copy_piece(stage, Q, prev_total.tail, G + H + pad, fill, a.out, a.out_capacity, tid);
                 tail_byte = (G + H + pad) >> 3;
             }
-#ifdef HB_DBG_SLOTS
-            if (tid == 0 && prev_tile == 387) printf("dbg CO: G %llu H %u tail %u hb %u stage[H>>5 -1..+1] %08x %08x %08x fill %x\n", (unsigned long long)G, H, prev_total.tail, prev_total.hb, stage[(H >> 5) - 1], stage[H >> 5], stage[(H >> 5) + 1], fill);
-#endif
             const uint64_t s0 = (uint64_t)prev_tile * kSlotsPerTile;
             for (uint64_t i = (uint64_t)prev_tf0 + tid; i < prev_tf1; i += kEncThreads) {
                 const uint32_t sp = (uint32_t)(a.slot_base[i] - s0);
@@ -454,9 +450,6 @@ __global__ void __launch_bounds__(kEncBlock, 2) encode_slots_kernel(const uint2 
             if (k == 20 && next_valid) prepare_fetch(next);
             enc_append(sp, acc, nb, c[k], l[k]);
         }
-#ifdef HB_DBG_SLOTS
-        if (false) printf("dbg tile %u tid %u nvalid %u pos0 %u Q %u H %u acc %08x nb %08x sp-first %d l26 %x l29 %x c26 %x c29 %x l30 %x l31 %x last %d in_tail %d\n", tile, tid, nvalid, pos0, Q, H, acc, nb, (int)(sp - sp_first), l[26], l[29], c[26], c[29], l[30], l[31], (int)last_slot, (int)in_tail);
-#endif
         {
             // the last slot of an item pads it with the LOW bits of eos_padding (huffman.c:178-184) — unless the
             // item lies in piece 0, whose padding depends on G and is added by the copy, or it is the tile's
@@ -464,9 +457,6 @@ __global__ void __launch_bounds__(kEncBlock, 2) encode_slots_kernel(const uint2 
             const uint32_t pad = (last_slot && in_tail && tid + 1 < nvalid) ? (0u - nb) & 7u : 0u;
             enc_append(sp, acc, nb, a.eos_padding & ((1u << pad) - 1u), enc_len_fields(pad));
         }
-#ifdef HB_DBG_SLOTS
-        if (false) printf("dbg after pad: acc %08x nb %08x sp-first %d word[-1] %08x\n", acc, nb, (int)(sp - sp_first), stage[((sp - stage_addr) >> 2) - 1]);
-#endif
         // The word I share with my predecessor(s); the thread that opens piece 1 puts what came before into
         // the last word of piece 0 instead.
         {
@@ -478,9 +468,6 @@ __global__ void __launch_bounds__(kEncBlock, 2) encode_slots_kernel(const uint2 
             if (any != 0xffffffffu) enc_seg_or_scan(v, f, lane);
             uint32_t cin = __shfl_up_sync(0xffffffffu, v, 1);
             if (lane == 0) cin = 0;
-#ifdef HB_DBG_SLOTS
-            if (tile == 387 && tid < 5) printf("dbg merge tile %u tid %u pos0 %u H %u Q %u v %08x rem %u brk %u any %08x cin %08x tstar %d hb %u exhb %u nsymflag %d\n", tile, tid, pos0, H, Q, v, rem, brk, any, cin, (int)tstar, mine.hb, excl.hb, (int)last_slot);
-#endif
             if (tstar) {
                 if ((H & 31u) && lane > 0) stage[H >> 5] = cin;  // (a zero leftover must be stored too: nothing else writes that word)
             } else if (brk && cin) {

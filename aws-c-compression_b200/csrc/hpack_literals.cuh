@@ -30,6 +30,30 @@ __device__ __forceinline__ uint32_t hpack_prefix_bytes(uint64_t len) {
     return nb;
 }
 
+// One warp copies n bytes, any alignment on either side: destination words are whole 32-bit stores, each made of
+// the two aligned source words that cover it (one funnel shift); only the ragged ends go byte by byte. Reads
+// stay inside the aligned words that hold the first and the last source byte.
+__device__ __forceinline__ void warp_copy_bytes(uint8_t *dst, const uint8_t *src, uint64_t n, uint32_t lane) {
+    if (n < 16) {
+        if (lane < n) dst[lane] = src[lane];
+        return;
+    }
+    const uint32_t head = (4u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 3)) & 3u;
+    if (lane < head) dst[lane] = src[lane];
+    const uint64_t words = (n - head) >> 2;
+    const uintptr_t s0 = reinterpret_cast<uintptr_t>(src) + head;
+    const uint32_t *sw = reinterpret_cast<const uint32_t *>(s0 & ~uintptr_t(3));
+    const uint32_t r8 = (uint32_t)(s0 & 3) * 8u;
+    uint32_t *dw = reinterpret_cast<uint32_t *>(dst + head);
+    for (uint64_t j = lane; j < words; j += 32) {
+        const uint32_t lo = sw[j];
+        const uint32_t hi = r8 ? sw[j + 1] : 0u;  // (not read when it could lie past the last source byte)
+        dw[j] = __funnelshift_r(lo, hi, r8);
+    }
+    const uint64_t tail0 = head + 4 * words;
+    if (lane < n - tail0) dst[tail0 + lane] = src[tail0 + lane];
+}
+
 // ---- encode ---------------------------------------------------------------------------------------------------
 // Per item: Huffman or not (mode), prefix size, frame size.
 __global__ void hpack_plan_kernel(
@@ -44,20 +68,38 @@ __global__ void hpack_plan_kernel(
     frame_lens[i] = hpack_prefix_bytes(payload) + payload;
 }
 
-// One warp per item: lane 0 writes the prefix, the warp copies the payload behind it. Never writes at or after
-// out + out_capacity.
+// A warp takes 32 literals: every lane looks up one of them (so the dependent loads of offsets and flags are paid
+// once per 32 items, not once per item) and writes its prefix; then the warp moves the 32 payloads one after the
+// other, all lanes on each. Never writes at or after out + out_capacity.
+struct MoveJob {
+    const uint8_t *src;
+    uint8_t *dst;
+    uint64_t len;
+};
+
+__device__ __forceinline__ void warp_run_jobs(MoveJob (*jobs)[32], const MoveJob &mine, uint32_t warp, uint32_t lane) {
+    jobs[warp][lane] = mine;
+    __syncwarp();
+#pragma unroll 1
+    for (int k = 0; k < 32; ++k) {
+        const MoveJob j = jobs[warp][k];
+        if (j.len) warp_copy_bytes(j.dst, j.src, j.len, lane);
+    }
+}
+
 __global__ void __launch_bounds__(256) hpack_frame_kernel(
     uint64_t n, const uint8_t *raw, const uint64_t *raw_offsets, const uint8_t *enc, const uint64_t *enc_offsets,
     const uint8_t *huff, uint8_t *out, uint64_t out_capacity, const uint64_t *out_offsets) {
-    const uint64_t i = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (i >= n) return;
-    const uint32_t lane = lane_id();
-    const bool h = huff[i] != 0;
-    const uint8_t *src = h ? enc + enc_offsets[i] : raw + raw_offsets[i];
-    const uint64_t len = h ? enc_offsets[i + 1] - enc_offsets[i] : raw_offsets[i + 1] - raw_offsets[i];
-    const uint64_t o0 = out_offsets[i];
-    const uint32_t np = hpack_prefix_bytes(len);
-    if (lane == 0) {
+    __shared__ MoveJob s_jobs[8][32];
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    const uint64_t i = ((uint64_t)blockIdx.x * 8 + warp) * 32 + lane;
+    MoveJob job = {nullptr, nullptr, 0};
+    if (i < n) {
+        const bool h = huff[i] != 0;
+        const uint8_t *src = h ? enc + enc_offsets[i] : raw + raw_offsets[i];
+        const uint64_t len = h ? enc_offsets[i + 1] - enc_offsets[i] : raw_offsets[i + 1] - raw_offsets[i];
+        const uint64_t o0 = out_offsets[i];
+        const uint32_t np = hpack_prefix_bytes(len);
         const uint8_t hbit = h ? 0x80 : 0x00;
         if (len < 127) {
             if (o0 < out_capacity) out[o0] = hbit | (uint8_t)len;
@@ -72,11 +114,12 @@ __global__ void __launch_bounds__(256) hpack_frame_kernel(
             }
             if (p < out_capacity) out[p] = (uint8_t)rem;
         }
+        const uint64_t room = o0 + np < out_capacity ? out_capacity - (o0 + np) : 0;
+        job.src = src;
+        job.dst = out + o0 + np;
+        job.len = min(len, room);
     }
-    uint8_t *dst = out + o0 + np;
-    const uint64_t room = o0 + np < out_capacity ? out_capacity - (o0 + np) : 0;
-    const uint64_t ncopy = min(len, room);
-    for (uint64_t k = lane; k < ncopy; k += 32) dst[k] = src[k];
+    warp_run_jobs(s_jobs, job, warp, lane);
 }
 
 // ---- decode ---------------------------------------------------------------------------------------------------
@@ -127,32 +170,37 @@ __global__ void hpack_parse_kernel(
     status[i] = st;
 }
 
-// One warp per item: dst[dst_offsets[i] ..) = the item's payload, taken from `alt` (packed, alt_offsets) when
-// pick[i] != 0, else from the framed input behind its prefix. skip_unpicked: items with pick[i] == 0 are left
-// out (the gather of Huffman payloads); otherwise they are copied as they are (raw literals in the final pass).
+// dst[dst_offsets[i] ..) = the item's payload, taken from `alt` (packed, alt_offsets) when pick[i] != 0, else from
+// the framed input behind its prefix. skip_unpicked: items with pick[i] == 0 are left out (the gather of Huffman
+// payloads); otherwise they are copied as they are (raw literals in the final pass). 32 items per warp, as above.
 __global__ void __launch_bounds__(256) hpack_move_kernel(
     uint64_t n, const uint8_t *framed, const uint64_t *framed_offsets, const uint8_t *prefix_len, const uint64_t *pay_lens,
     const uint8_t *alt, const uint64_t *alt_offsets, const uint8_t *pick, bool pick_from_alt, bool skip_unpicked,
     const int32_t *status, uint8_t *dst, uint64_t dst_capacity, const uint64_t *dst_offsets) {
-    const uint64_t i = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (i >= n) return;
-    if (status[i] != kStatusOk) return;
-    const bool picked = pick[i] != 0;
-    if (!picked && skip_unpicked) return;
-    const uint8_t *src;
-    uint64_t len;
-    if (picked && pick_from_alt) {
-        src = alt + alt_offsets[i];
-        len = alt_offsets[i + 1] - alt_offsets[i];
-    } else {
-        src = framed + framed_offsets[i] + prefix_len[i];
-        len = pay_lens[i];
+    __shared__ MoveJob s_jobs[8][32];
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    const uint64_t i = ((uint64_t)blockIdx.x * 8 + warp) * 32 + lane;
+    MoveJob job = {nullptr, nullptr, 0};
+    if (i < n && status[i] == kStatusOk) {
+        const bool picked = pick[i] != 0;
+        if (picked || !skip_unpicked) {
+            const uint8_t *src;
+            uint64_t len;
+            if (picked && pick_from_alt) {
+                src = alt + alt_offsets[i];
+                len = alt_offsets[i + 1] - alt_offsets[i];
+            } else {
+                src = framed + framed_offsets[i] + prefix_len[i];
+                len = pay_lens[i];
+            }
+            const uint64_t o0 = dst_offsets[i];
+            const uint64_t room = o0 < dst_capacity ? dst_capacity - o0 : 0;
+            job.src = src;
+            job.dst = dst + o0;
+            job.len = min(len, room);
+        }
     }
-    const uint64_t o0 = dst_offsets[i];
-    const uint64_t room = o0 < dst_capacity ? dst_capacity - o0 : 0;
-    const uint64_t ncopy = min(len, room);
-    const uint32_t lane = lane_id();
-    for (uint64_t k = lane; k < ncopy; k += 32) dst[o0 + k] = src[k];
+    warp_run_jobs(s_jobs, job, warp, lane);
 }
 
 // After the Huffman payloads were decoded (packed, dec_offsets; leftover register per item): the padding rule,

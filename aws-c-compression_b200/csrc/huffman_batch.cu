@@ -320,11 +320,8 @@ int encode_on_device(
 }
 
 // Packed layout, many strings: fused count -> look-back -> write kernel (one thread per string).
-int decode_batch_fast(aws_huffman_batch_ctx *ctx, Scratch &sc, const hb::BatchView &v, cudaStream_t stream) {
-    const uint64_t num_tiles = (v.n + kDecItemsPerTile - 1) / kDecItemsPerTile;
-    const size_t state_bytes = num_tiles * sizeof(uint64_t) + 256;
-    HB_CUDA_TRY(sc.tile_state.reserve(state_bytes));
-    HB_CUDA_TRY(cudaMemsetAsync(sc.tile_state.ptr, 0, state_bytes, stream));
+int decode_batch_fast(
+    aws_huffman_batch_ctx *ctx, Scratch &sc, const hb::BatchView &v, uint64_t total_in, cudaStream_t stream) {
     DecBatchArgs a{};
     a.b = v;
     a.lut = ctx->tables.lut;
@@ -332,9 +329,6 @@ int decode_batch_fast(aws_huffman_batch_ctx *ctx, Scratch &sc, const hb::BatchVi
     a.root_bits = ctx->tables.lut_root_bits;
     a.min_len = std::max<uint32_t>(1, ctx->tables.min_len);
     if (const char *exp = getenv("AWS_HUFFMAN_BATCH_EXPERIMENT")) a.debug = (uint32_t)atoi(exp);
-    a.tile_state = sc.tile_state.as<uint64_t>();
-    a.ticket = reinterpret_cast<uint32_t *>(a.tile_state + num_tiles);
-    a.num_tiles = (uint32_t)num_tiles;
     // Shared memory of one block (two blocks per SM): [LUT][stage][rows]. A string of L bytes decodes to at
     // most 8 L / min_len symbols, so the row area is that much larger than the stage; and the dense output
     // image (which reuses the stage and the front of the rows) must end before row offset `front`
@@ -349,6 +343,22 @@ int decode_batch_fast(aws_huffman_batch_ctx *ctx, Scratch &sc, const hb::BatchVi
     rows_bytes = std::min(rows_bytes, stage_bytes + front - 64) & ~size_t(15);
     a.stage_words = (uint32_t)(stage_bytes / 4 - 2);
     a.rows_bytes = (uint32_t)rows_bytes;
+    // strings per tile: as many as fit the stage and the row area at the batch's average length (with 12 % to
+    // spare for tiles above the average), in whole warps
+    {
+        const double avg = std::max(1.0, (double)total_in / (double)v.n);
+        const double by_stage = (double)(stage_bytes - 64) / (1.12 * avg);
+        const double by_rows = (double)rows_bytes / (1.12 * avg * expand + kDecRowSlack);
+        const uint64_t fit = (uint64_t)std::max(32.0, std::min(by_stage, by_rows));
+        a.items_per_tile = (uint32_t)std::min<uint64_t>(kDecItemsPerTile, fit & ~uint64_t(31));
+    }
+    const uint64_t num_tiles = (v.n + a.items_per_tile - 1) / a.items_per_tile;
+    const size_t state_bytes = num_tiles * sizeof(uint64_t) + 256;
+    HB_CUDA_TRY(sc.tile_state.reserve(state_bytes));
+    HB_CUDA_TRY(cudaMemsetAsync(sc.tile_state.ptr, 0, state_bytes, stream));
+    a.tile_state = sc.tile_state.as<uint64_t>();
+    a.ticket = reinterpret_cast<uint32_t *>(a.tile_state + num_tiles);
+    a.num_tiles = (uint32_t)num_tiles;
     const size_t smem = lut_bytes + ((stage_bytes + 15) & ~size_t(15)) + rows_bytes + 64;
     HB_CUDA_TRY(cudaFuncSetAttribute(decode_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned blocks = (unsigned)std::min<uint64_t>(num_tiles, (uint64_t)ctx->sm_count * 2);
@@ -456,7 +466,7 @@ int decode_on_device(
     const bool force_generic = getenv("AWS_HUFFMAN_BATCH_FORCE_GENERIC") != nullptr;
     if (!v.resume && !v.out_caps && ctx->tables.lut_count <= kDecLutMaxSmem && !force_generic) {
         if (v.n == 1 && total_in >= kStreamMinBytes) return decode_stream_fast(ctx, sc, v, total_in, stream);
-        return decode_batch_fast(ctx, sc, v, stream);
+        return decode_batch_fast(ctx, sc, v, total_in, stream);
     }
     if (!v.out_lens) {
         HB_CUDA_TRY(sc.lens.reserve(v.n * sizeof(uint64_t)));
@@ -809,7 +819,7 @@ int hpack_encode_on_device(
     aws_huffman_batch_ctx *ctx, uint64_t n, const uint8_t *raw, const uint64_t *raw_off, uint64_t total_in, uint32_t mode,
     uint8_t *out, uint64_t out_capacity, uint64_t *out_off, cudaStream_t st) {
     if (n == 0) return AWS_OP_SUCCESS;
-    const unsigned flat = (unsigned)((n + 255) / 256), warps = (unsigned)((n + 7) / 8);
+    const unsigned flat = (unsigned)((n + 255) / 256), warps = (unsigned)((n + 255) / 256);  // (move kernels: 32 items per warp)
     HB_CUDA_TRY(ctx->hp_huff.reserve(n));
     HB_CUDA_TRY(ctx->hp_lens.reserve(n * sizeof(uint64_t)));
     const uint8_t *pay = nullptr;
@@ -842,7 +852,7 @@ int hpack_decode_on_device(
     aws_huffman_batch_ctx *ctx, uint64_t n, const uint8_t *in, const uint64_t *in_off, uint64_t total_in, uint8_t *out,
     uint64_t out_capacity, uint64_t *out_off, int32_t *status, cudaStream_t st) {
     if (n == 0) return AWS_OP_SUCCESS;
-    const unsigned flat = (unsigned)((n + 255) / 256), warps = (unsigned)((n + 7) / 8);
+    const unsigned flat = (unsigned)((n + 255) / 256), warps = (unsigned)((n + 255) / 256);  // (move kernels: 32 items per warp)
     const uint32_t min_len = std::max<uint32_t>(1, ctx->tables.min_len);
     const uint64_t dec_cap = total_in * 8 / min_len + 64;
     HB_CUDA_TRY(ctx->hp_huff.reserve(n));

@@ -537,6 +537,16 @@ def test_batch_decode_with_oversized_strings(contexts, oracle, oracle_tables):
     _check_packed_encode_and_roundtrip(ctx, oracle, table, data, offs)
 
 
+@pytest.mark.parametrize("lo,hi", [(200, 256), (600, 900), (1, 6), (2000, 2400)])
+def test_batch_decode_string_length_regimes(contexts, oracle, oracle_tables, lo, hi):
+    """The batch decoder takes fewer strings per tile when the strings are long (so that a tile of average
+    strings still fits its shared-memory stage) and the full 288 when they are short."""
+    rng = np.random.default_rng(lo * 7 + hi)
+    ctx, table = contexts("hpack"), oracle_tables["hpack"]
+    data, offs = refcodec.random_batch(rng, 3000 if hi < 1000 else 700, lo, hi, "hpack")
+    _check_packed_encode_and_roundtrip(ctx, oracle, table, data, offs)
+
+
 def test_context_from_the_generators_code_table(pkg, coders, oracle, oracle_tables):
     """A context built from <name>_get_code_table() (no callbacks) encodes and decodes like the one built
     from <name>_get_coder()."""
