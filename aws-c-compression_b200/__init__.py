@@ -21,6 +21,7 @@ from .capi import (  # noqa: F401
     BatchContext,
     CodecError,
     Library,
+    TableBuilder,
     coders_library,
     product_library,
 )

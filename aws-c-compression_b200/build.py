@@ -37,6 +37,7 @@ C_SOURCES = [
     os.path.join(PKG, "host", "compression.c"),
     os.path.join(PKG, "host", "huffman_testing.c"),
     os.path.join(PKG, "host", "huffman_lut.c"),
+    os.path.join(PKG, "host", "huffman_table_builder.c"),
     os.path.join(ROOT, "shim", "aws-c-common", "source", "common_shim.c"),
 ]
 CU_SOURCES = [os.path.join(PKG, "csrc", "huffman_batch.cu")]

@@ -78,6 +78,11 @@ class aws_huffman_batch(C.Structure):
     ]
 
 
+class aws_huffman_table_coder(C.Structure):
+    _fields_ = [("coder", aws_huffman_symbol_coder), ("codes", aws_huffman_code * 256),
+                ("lut_entries", C.c_void_p), ("lut_count", C.c_uint32), ("lut_root_bits", C.c_uint8)]
+
+
 def python_coder(encode, decode=None):
     """A symbol coder backed by Python callables (tests only).
     encode(sym) -> (pattern, num_bits); decode(bits) -> (symbol, num_bits) or None."""
@@ -114,6 +119,9 @@ EXPORTED_SYMBOLS = [
     "aws_huffman_decode_batch", "aws_huffman_encode_batch_device", "aws_huffman_decode_batch_device",
     "aws_huffman_encode_batch_resume", "aws_huffman_decode_batch_resume",
     "aws_huffman_encode_batch_resume_device", "aws_huffman_decode_batch_resume_device",
+    "aws_huffman_histogram", "aws_huffman_histogram_device", "aws_huffman_code_lengths_from_counts",
+    "aws_huffman_canonical_codes", "aws_huffman_code_table_from_counts", "aws_huffman_code_table_write_def",
+    "aws_huffman_table_coder_init", "aws_huffman_table_coder_clean_up",
     "aws_hpack_string_encode_batch", "aws_hpack_string_decode_batch",
     "aws_hpack_string_encode_batch_device", "aws_hpack_string_decode_batch_device",
     "aws_huffman_get_encoded_length_batch", "aws_huffman_batch_ctx_synchronize",
@@ -229,6 +237,78 @@ class Library:
 
 _product = None
 _coders = None
+
+
+class TableBuilder:
+    """include/aws/compression/huffman_table_builder.h through ctypes (tests and tools)."""
+
+    def __init__(self, library=None):
+        self.library = library or product_library()
+        L, P = self.library.lib, C.POINTER
+        L.aws_huffman_histogram.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.c_void_p]
+        L.aws_huffman_histogram_device.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+        L.aws_huffman_code_lengths_from_counts.argtypes = [C.c_void_p, C.c_uint, C.c_bool, C.c_bool, C.c_void_p, P(C.c_uint8)]
+        L.aws_huffman_canonical_codes.argtypes = [C.c_void_p, C.c_uint8, C.c_void_p, P(aws_huffman_code)]
+        L.aws_huffman_code_table_from_counts.argtypes = [C.c_void_p, C.c_uint, C.c_bool, C.c_bool, C.c_void_p, P(aws_huffman_code)]
+        L.aws_huffman_code_table_write_def.argtypes = [C.c_void_p, C.c_char_p]
+        L.aws_huffman_table_coder_init.argtypes = [P(aws_huffman_table_coder), C.c_void_p]
+        L.aws_huffman_table_coder_clean_up.argtypes = [P(aws_huffman_table_coder)]
+        L.aws_huffman_table_coder_clean_up.restype = None
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise CodecError(self.library.last_error(), what)
+
+    def histogram(self, data, device=0):
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        counts = np.zeros(256, dtype=np.uint64)
+        self._check(self.library.lib.aws_huffman_histogram(device, data.ctypes.data, len(data), counts.ctypes.data),
+                    "aws_huffman_histogram")
+        return counts
+
+    def histogram_device(self, tensor, counts_tensor, stream=None):
+        self._check(self.library.lib.aws_huffman_histogram_device(tensor.data_ptr(), tensor.numel(), counts_tensor.data_ptr(),
+                                                                  stream or 0), "aws_huffman_histogram_device")
+
+    def lengths(self, counts, max_bits=32, cover_all=True, reserve_eos=False):
+        counts = np.ascontiguousarray(counts, dtype=np.uint64)
+        lens = np.zeros(256, dtype=np.uint8)
+        eos = C.c_uint8(0)
+        self._check(self.library.lib.aws_huffman_code_lengths_from_counts(counts.ctypes.data, max_bits, cover_all, reserve_eos,
+                                                                          lens.ctypes.data, C.byref(eos)),
+                    "aws_huffman_code_lengths_from_counts")
+        return lens, eos.value
+
+    def codes(self, counts, max_bits=32, cover_all=True, reserve_eos=False):
+        """Returns (aws_huffman_code[256] ctypes array, eos aws_huffman_code)."""
+        counts = np.ascontiguousarray(counts, dtype=np.uint64)
+        table = (aws_huffman_code * 256)()
+        eos = aws_huffman_code()
+        self._check(self.library.lib.aws_huffman_code_table_from_counts(counts.ctypes.data, max_bits, cover_all, reserve_eos,
+                                                                        C.cast(table, C.c_void_p), C.byref(eos)),
+                    "aws_huffman_code_table_from_counts")
+        return table, eos
+
+    def canonical(self, lengths, eos_length=0):
+        lengths = np.ascontiguousarray(lengths, dtype=np.uint8)
+        table = (aws_huffman_code * 256)()
+        eos = aws_huffman_code()
+        self._check(self.library.lib.aws_huffman_canonical_codes(lengths.ctypes.data, eos_length, C.cast(table, C.c_void_p),
+                                                                 C.byref(eos)), "aws_huffman_canonical_codes")
+        return table, eos
+
+    def write_def(self, table, path):
+        self._check(self.library.lib.aws_huffman_code_table_write_def(C.cast(table, C.c_void_p), path.encode()),
+                    "aws_huffman_code_table_write_def")
+
+    def table_coder(self, table):
+        coder = aws_huffman_table_coder()
+        self._check(self.library.lib.aws_huffman_table_coder_init(C.byref(coder), C.cast(table, C.c_void_p)),
+                    "aws_huffman_table_coder_init")
+        return coder
+
+    def table_coder_clean_up(self, coder):
+        self.library.lib.aws_huffman_table_coder_clean_up(C.byref(coder))
 
 
 def product_library():

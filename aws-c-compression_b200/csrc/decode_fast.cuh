@@ -470,7 +470,9 @@ template <bool kEmit, bool kPadded, bool kSkipHoles>
 __device__ __forceinline__ SpanS decode_span_smem(
     const uint32_t *s_in, const uint32_t *s_lut, uint32_t root_bits, uint32_t pos, uint32_t stop, uint32_t end,
     uint32_t out_addr) {
+#if !HB_DEC_UNIFIED
     constexpr int kSteps = 6;
+#endif
     constexpr uint32_t kParked = 0x80000000u;  // positions are far below 2^31: a parked lane fails "pos < pair_end"
     const uint32_t out0 = out_addr;
     SpanS r;

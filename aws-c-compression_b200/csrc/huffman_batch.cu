@@ -6,6 +6,7 @@
 // AWS_ERROR_COMPRESSION_DEVICE_FAILURE.
 #include <aws/compression/huffman_batch.h>
 #include <aws/compression/hpack_string_batch.h>
+#include <aws/compression/huffman_table_builder.h>
 
 #include "../host/huffman_lut.h"
 #include "device_common.cuh"
@@ -950,6 +951,66 @@ int hpack_run_host(
     return AWS_OP_SUCCESS;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Byte histogram (the counts a code table is built from). HBM-bound by construction: 16 bytes per
+// lane and load, and a block-wide histogram with ONE COLUMN PER LANE (hist[value][lane]): the 32 lanes of a
+// shared-memory atomic never meet in an address and every lane stays in its own bank, however skewed the
+// data is (the benchmark's top symbol is 40 % of the bytes: per-warp histograms would serialise 13-fold).
+// ---------------------------------------------------------------------------------------------
+constexpr int kHistThreads = 512;
+
+__global__ void __launch_bounds__(kHistThreads) histogram_kernel(const uint8_t *in, uint64_t size, unsigned long long *counts) {
+    __shared__ uint32_t s_hist[256 * 32];
+    for (uint32_t i = threadIdx.x; i < 256 * 32; i += kHistThreads) s_hist[i] = 0;
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t *const mine = s_hist + lane;
+    const uintptr_t base = reinterpret_cast<uintptr_t>(in);
+    const uint64_t head = min((unsigned long long)size, (unsigned long long)((16 - (base & 15)) & 15));  // bytes before the first aligned 16
+    const uint64_t nvec = (size - head) >> 4;
+    const uint4 *v = reinterpret_cast<const uint4 *>(in + head);
+    auto add_word = [&](uint32_t w) {
+        atomicAdd(mine + ((w & 0xffu) << 5), 1u);
+        atomicAdd(mine + (((w >> 8) & 0xffu) << 5), 1u);
+        atomicAdd(mine + (((w >> 16) & 0xffu) << 5), 1u);
+        atomicAdd(mine + ((w >> 24) << 5), 1u);
+    };
+    for (uint64_t i = (uint64_t)blockIdx.x * kHistThreads + threadIdx.x; i < nvec; i += (uint64_t)gridDim.x * kHistThreads) {
+        const uint4 q = __ldg(v + i);
+        add_word(q.x);
+        add_word(q.y);
+        add_word(q.z);
+        add_word(q.w);
+    }
+    if (blockIdx.x == 0) {  // the ragged ends
+        const uint64_t tail0 = head + 16 * nvec;
+        for (uint64_t i = threadIdx.x; i < head; i += kHistThreads) atomicAdd(mine + ((uint32_t)in[i] << 5), 1u);
+        for (uint64_t i = tail0 + threadIdx.x; i < size; i += kHistThreads) atomicAdd(mine + ((uint32_t)in[i] << 5), 1u);
+    }
+    __syncthreads();
+    // 256 values x 32 columns -> one count per value (a warp per value, 16 values per warp)
+    for (uint32_t value = threadIdx.x >> 5; value < 256; value += kHistThreads / 32) {
+        uint32_t c = s_hist[value * 32 + lane];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+        if (lane == 0 && c) atomicAdd(counts + value, (unsigned long long)c);
+    }
+}
+
+int histogram_on_device(const uint8_t *in, uint64_t size, uint64_t *counts, cudaStream_t st) {
+    HB_CUDA_TRY(cudaMemsetAsync(counts, 0, 256 * sizeof(uint64_t), st));
+    if (size == 0) return AWS_OP_SUCCESS;
+    int device = 0, sms = 148;
+    HB_CUDA_TRY(cudaGetDevice(&device));
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    // (a block's 32-bit columns hold its share of the bytes: size / blocks / 32 per column at most)
+    const uint64_t want = (size / 16 + kHistThreads - 1) / kHistThreads;
+    const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)sms * 4));
+    histogram_kernel<<<blocks, kHistThreads, 0, st>>>(in, size, reinterpret_cast<unsigned long long *>(counts));
+    HB_CUDA_TRY(cudaGetLastError());
+    return AWS_OP_SUCCESS;
+}
+
 __global__ void encoded_length_kernel(hb::DeviceTables t, const uint8_t *in, const uint64_t *in_offsets, uint64_t n, uint64_t *lens) {
     __shared__ uint32_t s_len[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_len[i] = t.enc[i].y;
@@ -1203,6 +1264,38 @@ int aws_huffman_decode_batch_device(
     HB_CUDA_TRY(cudaSetDevice(ctx->device));
     cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
     return decode_on_device(ctx, ctx->scratch, make_view(batch), batch->in_size, st);
+}
+
+int aws_huffman_histogram_device(const uint8_t *in, uint64_t size, uint64_t *counts, void *cuda_stream) {
+    if (!counts || (size && !in)) return aws_raise_error(AWS_ERROR_INVALID_ARGUMENT);
+    return histogram_on_device(in, size, counts, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int aws_huffman_histogram(int device_id, const uint8_t *in, uint64_t size, uint64_t counts[256]) {
+    if (!counts || (size && !in)) return aws_raise_error(AWS_ERROR_INVALID_ARGUMENT);
+    HB_CUDA_TRY(cudaSetDevice(device_id));
+    uint8_t *d_in = nullptr;
+    uint64_t *d_counts = nullptr;
+    cudaStream_t st = nullptr;
+    int rc = AWS_OP_ERR;
+    do {
+        if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) break;
+        if (cudaMalloc(&d_counts, 256 * sizeof(uint64_t)) != cudaSuccess) break;
+        if (size && cudaMalloc(&d_in, size) != cudaSuccess) break;
+        if (size && cudaMemcpyAsync(d_in, in, size, cudaMemcpyHostToDevice, st) != cudaSuccess) break;
+        if (histogram_on_device(d_in, size, d_counts, st)) break;
+        if (cudaMemcpyAsync(counts, d_counts, 256 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st) != cudaSuccess) break;
+        if (cudaStreamSynchronize(st) != cudaSuccess) break;
+        rc = AWS_OP_SUCCESS;
+    } while (false);
+    if (d_in) cudaFree(d_in);
+    if (d_counts) cudaFree(d_counts);
+    if (st) cudaStreamDestroy(st);
+    if (rc) {
+        (void)cudaGetLastError();
+        return aws_raise_error(AWS_ERROR_COMPRESSION_DEVICE_FAILURE);
+    }
+    return AWS_OP_SUCCESS;
 }
 
 int aws_hpack_string_encode_batch(
