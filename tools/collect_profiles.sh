@@ -16,3 +16,13 @@ python bench.py > gpurun_out/r1/bench_hpack_batch.json 2> gpurun_out/r1/bench_hp
 python bench.py --workload stream > gpurun_out/r1/bench_stream.json 2> gpurun_out/r1/bench_stream.err
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r1/bench_reference.json 2> gpurun_out/r1/bench_reference.err
 tail -c 600 gpurun_out/r1/bench_hpack_batch.json
+# the widened rows: histogram and literal framing kernels
+ncu --set full --clock-control none --import-source on -k regex:"histogram_kernel" -s 3 -c 1 -o gpurun_out/r1/histogram -f \
+    python tools/histogram_probe.py > /dev/null 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"hb::" -c 200 --csv --log-file gpurun_out/r1/launches_literals.csv \
+    python tools/literals_probe.py > /dev/null 2>&1
+python tools/histogram_probe.py > gpurun_out/r1/histogram.json 2>/dev/null
+python tools/literals_probe.py > gpurun_out/r1/literals.json 2>/dev/null
+# BASELINE config 5's share of one GPU: 8M strings (64M over 8 GPUs)
+python bench.py --strings 8000000 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r1/bench_8M_strings.json 2> gpurun_out/r1/bench_8M_strings.err
+tail -c 400 gpurun_out/r1/bench_8M_strings.json; tail -3 gpurun_out/r1/bench_8M_strings.err
