@@ -112,7 +112,7 @@ struct EncSlotMap {
 constexpr size_t kEncSlotSmemBytes =
     kEncStageWords * 4 + (kSlotsPerTile + 4) * 2 /* item start positions */ + 2048 * kEncTabCopies /* code table */ + kSlotSymBytes;
 
-__global__ void HB_ENC_KERNEL_BOUNDS encode_slots_kernel(const uint2 *__restrict__ enc_table, EncSlotArgs a) {
+__global__ void __launch_bounds__(kEncBlock, 2) encode_slots_kernel(const uint2 *__restrict__ enc_table, EncSlotArgs a) {
     __shared__ Seg s_wseg[kEncWarps];
     __shared__ uint32_t s_tail[kEncWarps], s_brk[kEncWarps], s_wpos[kEncWarps + 1];
     __shared__ uint32_t s_next;

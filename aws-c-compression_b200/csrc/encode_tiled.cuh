@@ -37,14 +37,6 @@
 
 #include "device_common.cuh"
 
-// Register budget of the encoder kernels (two blocks of 288 threads per SM either way). HB_ENC_MAXNREG: an explicit
-// cap instead of the launch bounds (A/B: does the compiler stop spilling with 112 registers?).
-#ifdef HB_ENC_MAXNREG
-#define HB_ENC_KERNEL_BOUNDS __maxnreg__(HB_ENC_MAXNREG)
-#else
-#define HB_ENC_KERNEL_BOUNDS __launch_bounds__(kEncBlock, 2)
-#endif
-
 namespace hb {
 
 constexpr int kEncThreads = 256;
