@@ -33,6 +33,9 @@ namespace hb {
 #ifndef HB_DEC_UNIFIED
 #define HB_DEC_UNIFIED 1  // 1: links are followed inside the ordinary steps; 0: lanes park and walk once per round
 #endif
+#ifndef HB_ROWCOPY_BATCH
+#define HB_ROWCOPY_BATCH 1
+#endif
 #ifndef HB_DEC_UNIFIED_STEPS
 #define HB_DEC_UNIFIED_STEPS 6
 #endif
@@ -688,7 +691,20 @@ __device__ __forceinline__ void smem_copy_row(const uint8_t *src, uint8_t *dst, 
         uint32_t *dw = reinterpret_cast<uint32_t *>(dst + head);
         const uint32_t sel = 0x3210u + 0x1111u * head;  // bytes head .. head + 3 of a word pair
         uint32_t lo = sw[0];
-        for (uint32_t j = 0; j < body; ++j) {
+        uint32_t j = 0;
+#if HB_ROWCOPY_BATCH
+        // four loads in flight before the four stores (source and destination never overlap within a phase, but
+        // the compiler cannot know and would keep every load behind the previous store)
+        for (; j + 4 <= body; j += 4) {
+            const uint32_t h0 = sw[j + 1], h1 = sw[j + 2], h2 = sw[j + 3], h3 = sw[j + 4];
+            dw[j] = __byte_perm(lo, h0, sel);
+            dw[j + 1] = __byte_perm(h0, h1, sel);
+            dw[j + 2] = __byte_perm(h1, h2, sel);
+            dw[j + 3] = __byte_perm(h2, h3, sel);
+            lo = h3;
+        }
+#endif
+        for (; j < body; ++j) {
             const uint32_t hi = sw[j + 1];
             dw[j] = __byte_perm(lo, hi, sel);
             lo = hi;
