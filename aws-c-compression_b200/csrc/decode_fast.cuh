@@ -1005,7 +1005,14 @@ __global__ void __launch_bounds__(kDecThreads, 2) decode_batch_kernel(DecBatchAr
 // occupies [begin_bit, end_bit) = [8 * lead, 8 * (lead + len)).
 // ---------------------------------------------------------------------------------------------
 constexpr uint32_t kChunkBits = 1024;   // 128 encoded bytes per thread
-constexpr uint32_t kPrerollBits = 256;  // HPACK on Zipf data: 99.4 % of starts are in sync by then
+// Pre-roll: HPACK on Zipf data is in sync after 256 bits for 99.4 % of the starts (longest seen:
+// 485), but a tile in which ONE chunk entered wrong pays a whole extra chunk decode with one lane working (the
+// others wait at the barrier), and at 256 bits 78 % of the 256-chunk tiles have such a chunk. Measured on the
+// 1 GiB stream: 256 bits 2.75 ms, 384 bits 2.47 ms, 512 bits 2.51 ms.
+#ifndef HB_PREROLL_BITS
+#define HB_PREROLL_BITS 384
+#endif
+constexpr uint32_t kPrerollBits = HB_PREROLL_BITS;
 constexpr int kStreamThreads = 256;
 constexpr uint32_t kStreamRowWords = 33;                                      // 32 words + 1 copy of the next row's first
 constexpr uint32_t kStreamStageWords = (kStreamThreads + 1) * kStreamRowWords + 1;  // previous chunk + 128 own
