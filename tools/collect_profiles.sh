@@ -26,3 +26,5 @@ python tools/literals_probe.py > gpurun_out/r1/literals.json 2>/dev/null
 # BASELINE config 5's share of one GPU: 8M strings (64M over 8 GPUs)
 python bench.py --strings 8000000 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r1/bench_8M_strings.json 2> gpurun_out/r1/bench_8M_strings.err
 tail -c 400 gpurun_out/r1/bench_8M_strings.json; tail -3 gpurun_out/r1/bench_8M_strings.err
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+python -m pytest tests -m gpu -x -q 2>&1 | tail -2
