@@ -30,9 +30,6 @@
 
 namespace hb {
 
-#ifndef HB_DEC_UNIFIED
-#define HB_DEC_UNIFIED 1  // 1: links are followed inside the ordinary steps; 0: lanes park and walk once per round
-#endif
 #ifndef HB_ROWCOPY_BATCH
 #define HB_ROWCOPY_BATCH 1
 #endif
@@ -294,17 +291,6 @@ struct WordWriter {
     }
 };
 
-// Emits symbols as single bytes into shared memory (a row that belongs to the emitting thread alone).
-// A two-symbol entry is two byte stores; nothing else is tracked (the count is the address difference).
-struct ByteEmitter {
-    uint32_t addr;  // shared-window byte address of the next symbol
-    template <bool kSecond>
-    __device__ __forceinline__ void put(uint32_t entry) {
-        asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(entry >> (kSecond ? 16 : 8)) : "memory");
-        ++addr;
-    }
-};
-
 struct SpanS {
     uint32_t pos;   // stage-relative bit position after the last decoded symbol
     uint32_t nsym;
@@ -418,9 +404,8 @@ __device__ __forceinline__ SpanS decode_smem(
 // The hot loop of the single-pass decoders: two symbols per lookup straight from the staged stream,
 // symbols emitted as bytes into the thread's shared-memory row. Hand-tightened (shared-window
 // addresses, PTX loads/stores) because this loop is most of the decode time:
-//   * a lane that meets a code longer than the root index PARKS by setting its position to ~0 (so the
-//     one loop test "pos < pair_end" also skips parked lanes); parked lanes are resolved together
-//     after kSteps steps
+//   * a lane that meets a code longer than the root index (a link) spends its NEXT step on the sub-table the
+//     link names, with its position unchanged: every step is one lookup, whatever the table
 //   * both symbol bytes of an entry are always stored and the address advances by the entry's count:
 //     no branch; a one-symbol entry leaves a stray byte that the next store overwrites (rows have room
 //     for one byte more than they can hold)
@@ -473,9 +458,6 @@ template <bool kEmit, bool kPadded, bool kSkipHoles>
 __device__ __forceinline__ SpanS decode_span_smem(
     const uint32_t *s_in, const uint32_t *s_lut, uint32_t root_bits, uint32_t pos, uint32_t stop, uint32_t end,
     uint32_t out_addr) {
-#if !HB_DEC_UNIFIED
-    constexpr int kSteps = 6;
-#endif
     constexpr uint32_t kParked = 0x80000000u;  // positions are far below 2^31: a parked lane fails "pos < pair_end"
     const uint32_t out0 = out_addr;
     SpanS r;
@@ -492,7 +474,6 @@ __device__ __forceinline__ SpanS decode_span_smem(
         const uint32_t shift = 32 - root_bits;
         StreamCursor c;
         c.init<kPadded>(in_addr, pos);
-#if HB_DEC_UNIFIED
         // Every step is ONE table lookup, whatever the table: a lane whose lookup returned a link (a code
         // longer than the root index: a few % of the symbols) keeps its position and spends its next step
         // on the sub-table the link names, while the other lanes carry on with their own symbols. No lane
@@ -546,63 +527,6 @@ __device__ __forceinline__ SpanS decode_span_smem(
             pos &= ~kParked;
             r.term = kTermUnknown;
         }
-#else
-        while (pos < pair_end) {
-            // Straight-line steps: a lane that is parked or past its end runs along with every update
-            // predicated off (its lookup reads some valid root entry and is ignored), so the warp never
-            // splits inside a round.
-#pragma unroll
-            for (int step = 0; step < kSteps; ++step) {
-                const uint32_t e = lds_u32(lut_addr + ((c.window(pos) >> shift) << 2));
-                const bool active = pos < pair_end;
-                const bool adv = active && dlut_is_leaf(e);
-                if (active && !dlut_is_leaf(e)) pos |= kParked;
-                if (adv) pos += e >> 24;
-                if (kEmit) {
-                    const uint32_t on = adv ? 1u : 0u;
-                    asm volatile(
-                        "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p st.shared.u8 [%0], %1;\n\t@p st.shared.u8 [%0+1], %2;\n\t}" ::"r"(out_addr),
-                        "r"(e >> 8), "r"(e >> 16), "r"(on)
-                        : "memory");
-                    if (adv) out_addr += e & 3u;
-                }
-                const bool cross = adv && (int)pos >= c.limit;
-                if (cross) {
-                    c.w0 = c.w1;
-                    c.w1 = c.w2;
-                    c.limit += 32;
-                }
-                {
-                    const uint32_t on = cross ? 1u : 0u;
-                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.shared.u32 %0, [%1];\n\t}"
-                                 : "+r"(c.w2)
-                                 : "r"(c.wa), "r"(on));
-                }
-                if (cross) c.wa += 4;
-            }
-            // codes longer than the root index (a few % of the symbols): the parked lanes walk the sub-tables
-            // together, once per round
-            if (pos & kParked) {
-                pos &= ~kParked;
-                const uint32_t window = c.window(pos);
-                const uint32_t e = dec_walk(s_lut, root_bits, window, s_lut[window >> shift]);
-                if (e == 0) {
-                    if (!kSkipHoles) {
-                        r.term = kTermUnknown;  // >= 32 real bits and no code matches
-                        break;
-                    }
-                    ++pos;
-                } else {
-                    pos += dlut_len1(e);
-                    if (kEmit) {
-                        sts_u8(out_addr, e >> 8);
-                        ++out_addr;
-                    }
-                }
-                c.follow(pos);
-            }
-        }
-#endif
         // the last few symbols of the span: one lookup at a time with the end-of-stream rules (the window is
         // the stream zero-extended, huffman.c:196-211; a code that does not fit ends the stream, :240-255).
         // A two-symbol entry still counts when its second code starts before `stop` and ends inside the stream.
@@ -845,14 +769,7 @@ __global__ void __launch_bounds__(kDecThreads, 2) decode_batch_kernel(DecBatchAr
                 uint32_t nsym, term;
                 if (staged) {
                     const uint32_t ib = s_start[it], ie = ib + nbytes * 8;
-                    SpanS r;
-                    if (a.debug & 2u) {
-                        ByteEmitter em;
-                        em.addr = rows_addr + s_row[it];
-                        r = decode_smem<true, false, false>(s_in, s_lut, a.root_bits, ib, ie, ie, &em);
-                    } else {
-                        r = decode_span_smem<true, false, false>(s_in, s_lut, a.root_bits, ib, ie, ie, rows_addr + s_row[it]);
-                    }
+                    const SpanS r = decode_span_smem<true, false, false>(s_in, s_lut, a.root_bits, ib, ie, ie, rows_addr + s_row[it]);
                     cbits = r.pos - ib;
                     nsym = r.nsym;
                     term = r.term;
