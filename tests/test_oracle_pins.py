@@ -194,3 +194,65 @@ def test_live_differential_against_reference(oracle, oracle_tables, ref, table_n
         b = ref.decode_batch(r_coder, payload, enc["out_offsets"], int(caps.sum()) + 1, out_offsets=slots, out_caps=caps)
         for k in a:
             assert np.array_equal(a[k], b[k]), k
+
+
+@pytest.mark.parametrize("table_name", ["test", "hpack"])
+def test_streaming_state_against_reference(oracle, oracle_tables, ref, pkg, table_name):
+    """The oracle's state ACROSS calls (encoder overflow bits, decoder register) against the unmodified
+    reference driven the same way: output in small pieces, input in small chunks (the reference's own
+    chunked tests, tests/huffman_test.c:117-165,275-363). This is what the *_resume GPU tests lean on."""
+    import ctypes as C
+    capi = pkg.capi
+    L = capi.bind_streaming_api(C.CDLL(refcodec.REF_SO))
+    coder = C.cast(ref.coder(table_name), C.POINTER(capi.aws_huffman_symbol_coder))
+    table = oracle_tables[table_name]
+    rng = np.random.default_rng(0xC0DE)
+
+    def ref_call(fn, state, data, cap):
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        out = np.zeros(max(cap, 1), dtype=np.uint8)
+        cur = capi.aws_byte_cursor(len(data), data.ctypes.data if len(data) else None)
+        buf = capi.aws_byte_buf(0, out.ctypes.data, cap, None)
+        L.aws_reset_error()
+        rc = fn(C.byref(state), C.byref(cur), C.byref(buf))
+        code = 0 if rc == 0 else L.aws_last_error()
+        return code, len(data) - cur.len, bytes(out[:buf.len])
+
+    for case in range(60):
+        text, _ = refcodec.random_batch(rng, 1, 0, 120, table_name)
+        cap = int(rng.integers(1, 9))
+        enc_r = capi.aws_huffman_encoder()
+        L.aws_huffman_encoder_init(C.byref(enc_r), coder)
+        enc_o = oracle.new_encoder(table, 0xFF)
+        pos, encoded = 0, b""
+        for _ in range(2000):
+            code, used, out_r = ref_call(L.aws_huffman_encode, enc_r, text[pos:], cap)
+            out_o = np.zeros(cap, dtype=np.uint8)
+            rc_o, used_o, len_o = oracle.encode_call(enc_o, text[pos:], out_o, 0, cap)
+            assert (rc_o, used_o, bytes(out_o[:len_o])) == (code, used, out_r), "encode case %d" % case
+            assert enc_o.overflow_bits.num_bits == enc_r.overflow_bits.num_bits
+            if enc_r.overflow_bits.num_bits:
+                assert enc_o.overflow_bits.pattern == enc_r.overflow_bits.pattern
+            pos += used
+            encoded += out_r
+            if code == OK:
+                break
+            assert code == SHORT_BUFFER
+        # decode: input in chunks of `step` bytes, output in pieces of `cap` bytes
+        step = int(rng.integers(1, 7))
+        stream = np.frombuffer(encoded, dtype=np.uint8)
+        dec_r = capi.aws_huffman_decoder()
+        L.aws_huffman_decoder_init(C.byref(dec_r), coder)
+        dec_o = oracle.new_decoder(table)
+        pos = fed = 0
+        for _ in range(5000):
+            if pos == fed:
+                fed = min(len(stream), fed + step)
+            code, used, out_r = ref_call(L.aws_huffman_decode, dec_r, stream[pos:fed], cap)
+            out_o = np.zeros(cap, dtype=np.uint8)
+            rc_o, used_o, len_o = oracle.decode_call(dec_o, stream[pos:fed], out_o, 0, cap)
+            assert (rc_o, used_o, bytes(out_o[:len_o])) == (code, used, out_r), "decode case %d" % case
+            assert (dec_o.working_bits, dec_o.num_bits) == (dec_r.working_bits, dec_r.num_bits)
+            pos += used
+            if code == OK and fed == len(stream) and pos == fed:
+                break
