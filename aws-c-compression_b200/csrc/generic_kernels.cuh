@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) encode_items_warp_kernel(
             if (flushed + nbytes > clip_bytes) nbytes = clip_bytes > flushed ? clip_bytes - flushed : 0;
             for (uint32_t i = lane; i < nbytes; i += 32) {
                 const uint8_t byte = (uint8_t)(stage[i >> 2] >> (24 - 8 * (i & 3)));
-                if (flushed + i < phys_room) dst[flushed + i] = byte;
+                if (kWrite && flushed + i < phys_room) dst[flushed + i] = byte;
             }
             const uint32_t whole = have_bits >> 3;
             const uint32_t carry_byte = (stage[whole >> 2] >> (24 - 8 * (whole & 3))) & 0xffu;
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) encode_items_warp_kernel(
         if (kWrite && carry) {
             const uint32_t pad = 8 - carry;
             const uint8_t last = (uint8_t)((stage[0] >> 24) | (t.eos_padding & ((1u << pad) - 1u)));
-            if (lane == 0 && flushed < phys_room) dst[flushed] = last;
+            if (kWrite && lane == 0 && flushed < phys_room) dst[flushed] = last;
         }
     }
 
