@@ -588,7 +588,6 @@ struct DecBatchArgs {
     uint32_t num_tiles;
     uint32_t items_per_tile;  // <= kDecItemsPerTile, a multiple of 32: fewer when the strings are long, so that a
                               // tile of average strings still fits the stage
-    uint32_t debug;  // AWS_HUFFMAN_BATCH_EXPERIMENT (A/B timing only)
     uint8_t *scratch;       // deferred output: one slot of scratch_slot bytes per block (16-byte aligned)
     uint32_t scratch_slot;
 };

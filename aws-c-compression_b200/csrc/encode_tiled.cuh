@@ -240,7 +240,6 @@ struct EncTiledArgs {
     uint32_t *ticket;
     uint32_t num_tiles;
     uint32_t eos_padding;
-    uint32_t debug;  // timing experiments only (AWS_HUFFMAN_BATCH_EXPERIMENT); results are wrong when set
 };
 
 // Shared-memory table entry of the tiled encoder: x = code, y = len | len << 27 (len <= 31).

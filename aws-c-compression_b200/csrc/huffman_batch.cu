@@ -251,7 +251,6 @@ int encode_tiled_on_device(
     a.ticket = reinterpret_cast<uint32_t *>(a.tile_state + num_tiles);
     a.num_tiles = (uint32_t)num_tiles;
     a.eos_padding = ctx->tables.eos_padding;
-    if (const char *exp = getenv("AWS_HUFFMAN_BATCH_EXPERIMENT")) a.debug = (uint32_t)atoi(exp);
     if (seg) {
         HB_CUDA_TRY(sc.tile_first.reserve((num_tiles + 1) * sizeof(uint32_t)));
         a.tile_first = sc.tile_first.as<uint32_t>();
@@ -329,7 +328,6 @@ int decode_batch_fast(
     a.lut_count = ctx->tables.lut_count;
     a.root_bits = ctx->tables.lut_root_bits;
     a.min_len = std::max<uint32_t>(1, ctx->tables.min_len);
-    if (const char *exp = getenv("AWS_HUFFMAN_BATCH_EXPERIMENT")) a.debug = (uint32_t)atoi(exp);
     // Shared memory of one block (two blocks per SM): [LUT][stage][rows]. A string of L bytes decodes to at
     // most 8 L / min_len symbols, so the row area is that much larger than the stage; and the dense output
     // image (which reuses the stage and the front of the rows) must end before row offset `front`
