@@ -652,6 +652,10 @@ __device__ __forceinline__ void smem_copy_row(const uint8_t *src, uint8_t *dst, 
 //      the others after a barrier (their destination may overlap rows that are already gone).
 // A tile whose strings do not fit the stage is decoded straight from global memory in two passes.
 // Dynamic shared memory: [LUT][stage words + 2][rows]
+// kFramed: the items are HPACK string literals (hpack_literals.cuh): the string table parses each literal's H bit and
+// length (the payload is what gets staged / decoded), raw literals are copied instead of decoded, and the padding rule
+// of RFC 7541 5.2 is applied to what the decoder leaves over; items with a non-zero status decode to nothing.
+template <bool kFramed>
 __global__ void __launch_bounds__(kDecThreads, 2) decode_batch_kernel(DecBatchArgs a) {
     extern __shared__ __align__(16) uint32_t s_lut[];  // [LUT][stage][rows]
     const uint32_t lut_pad = (a.lut_count + 3u) & ~3u;
@@ -665,6 +669,7 @@ __global__ void __launch_bounds__(kDecThreads, 2) decode_batch_kernel(DecBatchAr
     __shared__ uint32_t s_off[2][kDecItemsPerTile]; // exclusive offsets within the tile (this tile's and the pending one's)
     __shared__ uint32_t s_row[kDecItemsPerTile];    // start of the string's row in the row area
     __shared__ uint16_t s_perm[kDecItemsPerTile];   // strings in order of decreasing length
+    __shared__ uint8_t s_flag[kFramed ? kDecItemsPerTile : 1];  // framed: bit 0 raw payload, bit 1 malformed literal
     static_assert(kDecItemsPerTile <= 2 * kDecThreads, "the block scan handles two strings per thread");
     __shared__ uint32_t s_hist[256];
     __shared__ uint64_t s_warp_sum[kDecWarps];
@@ -707,8 +712,18 @@ __global__ void __launch_bounds__(kDecThreads, 2) decode_batch_kernel(DecBatchAr
         bool fits = nwords64 <= a.stage_words && rows_need <= a.rows_bytes;
         for (uint32_t it = threadIdx.x; it < nitems; it += kDecThreads) {
             const uint64_t in0 = b.in_offsets[item0 + it];
-            const uint64_t len = b.in_offsets[item0 + it + 1] - in0;
-            s_start[it] = (uint32_t)(in0 - byte0) * 8 + lead * 8;
+            uint64_t len = b.in_offsets[item0 + it + 1] - in0;
+            uint64_t skip = 0;  // bytes of the item before its payload
+            if (kFramed) {
+                uint32_t h, np;
+                uint64_t plen;
+                const int32_t st = hpack_parse_literal(b.in + in0, len, h, np, plen);
+                s_flag[it] = (uint8_t)((st != kStatusOk ? 2u : 0u) | (h ? 0u : 1u));
+                if (st != kStatusOk && b.status) b.status[item0 + it] = st;
+                len = st == kStatusOk ? plen : 0;
+                skip = np;
+            }
+            s_start[it] = (uint32_t)(in0 + skip - byte0) * 8 + lead * 8;
             s_bytes[it] = (uint32_t)min(len, (uint64_t)0xffffffffu);
             s_row[it] = 4 * (uint32_t)((2 * (in0 - byte0) + a.min_len - 1) / a.min_len) + kDecRowSlack * it;
             if (8 * len / a.min_len + kDecRowSlack > kDecMaxRow) s_fits = 0;
@@ -764,24 +779,49 @@ __global__ void __launch_bounds__(kDecThreads, 2) decode_batch_kernel(DecBatchAr
                 const uint32_t it = s_perm[slot];
                 const uint64_t item = item0 + it;
                 const uint32_t nbytes = s_bytes[it];
-                uint64_t cbits;
-                uint32_t nsym, term;
-                if (staged) {
+                uint64_t cbits = 0;
+                uint32_t nsym = 0, term = kTermEnd;
+                const uint32_t flag = kFramed ? s_flag[it] : 0u;
+                // (framed: where the payload starts in global memory; s_start holds it relative to the tile)
+                const uint8_t *payload = b.in + (kFramed ? byte0 + (s_start[it] >> 3) - lead : b.in_offsets[item]);
+                int32_t st = kStatusOk;
+                if (kFramed && flag != 0) {
+                    if (flag == 1u) {  // raw literal: the payload is the string
+                        nsym = nbytes;
+                        if (staged) {
+                            const uint32_t first = s_start[it] >> 3, row = rows_addr + s_row[it];
+                            for (uint32_t k = 0; k < nbytes; ++k)
+                                sts_u8(row + k, s_in[(first + k) >> 2] >> (24 - 8 * ((first + k) & 3)));
+                        }
+                    }
+                } else if (staged) {
                     const uint32_t ib = s_start[it], ie = ib + nbytes * 8;
                     const SpanS r = decode_span_smem<true, false, false>(s_in, s_lut, a.root_bits, ib, ie, ie, rows_addr + s_row[it]);
                     cbits = r.pos - ib;
                     nsym = r.nsym;
                     term = r.term;
+                    if (kFramed && term != kTermUnknown) {
+                        const uint32_t rem = ie - r.pos;  // what the decoder left over: must be < 8 bits, all ones
+                        if (rem >= 8u || (rem != 0u && (smem_window<false>(s_in, r.pos) >> (32u - rem)) != (1u << rem) - 1u))
+                            st = kStatusInvalidPadding;
+                    }
                 } else {
-                    const uint64_t in0 = b.in_offsets[item];
-                    const uint64_t len = b.in_offsets[item + 1] - in0;
-                    const DecodeSpan r = decode_span<false, false>(s_lut, a.root_bits, b.in + in0, 0, len * 8, len, nullptr);
+                    const uint64_t len = kFramed ? (uint64_t)nbytes : b.in_offsets[item + 1] - b.in_offsets[item];
+                    const DecodeSpan r = decode_span<false, false>(s_lut, a.root_bits, payload, 0, len * 8, len, nullptr);
                     cbits = r.pos;
                     nsym = (uint32_t)r.nsym;
                     term = r.term;
+                    if (kFramed && term != kTermUnknown) {
+                        uint64_t bits = 0;
+                        uint8_t nb = 0;
+                        leftover_state(payload, len, cbits, false, nullptr, &bits, &nb);
+                        if (!hpack_padding_ok(bits, nb)) st = kStatusInvalidPadding;
+                    }
                 }
+                if (term == kTermUnknown) st = kStatusUnknownSymbol;
+                if (kFramed && st != kStatusOk) nsym = 0;  // a literal that fails decodes to nothing
                 s_cnt[it] = nsym;
-                if (b.status) b.status[item] = term == kTermUnknown ? kStatusUnknownSymbol : kStatusOk;
+                if (b.status && !(kFramed && (flag & 2u))) b.status[item] = st;
                 if (b.consumed || b.leftover_working_bits || b.leftover_num_bits) {
                     const uint64_t in0 = b.in_offsets[item];
                     leftover_state(
@@ -889,12 +929,18 @@ __global__ void __launch_bounds__(kDecThreads, 2) decode_batch_kernel(DecBatchAr
                     const uint32_t it = s_perm[gslot];
                     const uint64_t off = tile_base + s_off[par][it];
                     const uint64_t room = off < b.out_capacity ? b.out_capacity - off : 0;
-                    const uint64_t in0 = b.in_offsets[item0 + it];
-                    const uint64_t len = b.in_offsets[item0 + it + 1] - in0;
-                    ByteWriter wr;
-                    wr.init(b.out + off, room);
-                    decode_span<true, false>(s_lut, a.root_bits, b.in + in0, 0, len * 8, len, &wr);
-                    wr.finish();
+                    const uint64_t in0 = kFramed ? byte0 + (s_start[it] >> 3) - lead : b.in_offsets[item0 + it];
+                    const uint64_t len = kFramed ? (uint64_t)s_bytes[it] : b.in_offsets[item0 + it + 1] - in0;
+                    if (kFramed && s_cnt[it] == 0) {
+                        // nothing to write (empty, malformed or failed literal)
+                    } else if (kFramed && (s_flag[it] & 1u)) {
+                        for (uint64_t k = 0; k < len && k < room; ++k) b.out[off + k] = b.in[in0 + k];
+                    } else {
+                        ByteWriter wr;
+                        wr.init(b.out + off, room);
+                        decode_span<true, false>(s_lut, a.root_bits, b.in + in0, 0, len * 8, len, &wr);
+                        wr.finish();
+                    }
                 }
                 uint32_t next = 0;
                 if (lane == 0) next = atomicAdd(&s_next, 1u);

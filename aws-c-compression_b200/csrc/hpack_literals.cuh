@@ -129,40 +129,48 @@ __global__ void __launch_bounds__(256) hpack_frame_kernel(
 //                                   bytes than it announces)
 //   AWS_ERROR_INVALID_ARGUMENT      bytes left over after the payload, or a length that does not fit 62 bits
 // gather_lens[i] = bytes of Huffman payload to decode (0 for raw and malformed items).
+// H bit, prefix integer (RFC 7541 5.1) and consistency of one literal of `size` bytes at p.
+__device__ __forceinline__ int32_t hpack_parse_literal(const uint8_t *p, uint64_t size, uint32_t &h, uint32_t &np, uint64_t &len) {
+    h = 0;
+    np = 0;
+    len = 0;
+    if (size == 0) return kStatusShortBuffer;
+    const uint8_t b0 = p[0];
+    h = b0 >> 7;
+    len = b0 & 127;
+    np = 1;
+    if (len == 127) {
+        uint32_t shift = 0;
+        bool more = true;
+        while (more) {
+            if (np >= size) return kStatusShortBuffer;
+            const uint8_t b = p[np];
+            ++np;
+            if (shift > 56) return kStatusInvalidArgument;
+            len += (uint64_t)(b & 127) << shift;
+            shift += 7;
+            more = (b & 128) != 0;
+        }
+    }
+    if (len > size - np) return kStatusShortBuffer;
+    if (len < size - np) return kStatusInvalidArgument;
+    return kStatusOk;
+}
+
+// The padding rule of section 5.2 on what a decoder left over: `nb` bits, left-aligned in `bits`.
+__device__ __forceinline__ bool hpack_padding_ok(uint64_t bits, uint32_t nb) {
+    return nb < 8 && (nb == 0 || (bits >> (64 - nb)) == ((1ull << nb) - 1));
+}
+
 __global__ void hpack_parse_kernel(
     uint64_t n, const uint8_t *in, const uint64_t *in_offsets, uint8_t *huff, uint8_t *prefix_len, uint64_t *pay_lens,
     uint64_t *gather_lens, int32_t *status) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint64_t a = in_offsets[i], size = in_offsets[i + 1] - a;
-    int32_t st = kStatusOk;
-    uint32_t h = 0, np = 0;
-    uint64_t len = 0;
-    if (size == 0) {
-        st = kStatusShortBuffer;
-    } else {
-        const uint8_t b0 = in[a];
-        h = b0 >> 7;
-        len = b0 & 127;
-        np = 1;
-        if (len == 127) {
-            uint32_t shift = 0;
-            bool more = true;
-            while (more) {
-                if (np >= size) { st = kStatusShortBuffer; break; }
-                const uint8_t b = in[a + np];
-                ++np;
-                if (shift > 56) { st = kStatusInvalidArgument; break; }
-                len += (uint64_t)(b & 127) << shift;
-                shift += 7;
-                more = (b & 128) != 0;
-            }
-        }
-        if (st == kStatusOk) {
-            if (len > size - np) st = kStatusShortBuffer;
-            else if (len < size - np) st = kStatusInvalidArgument;
-        }
-    }
+    uint32_t h, np;
+    uint64_t len;
+    const int32_t st = hpack_parse_literal(in + a, size, h, np, len);
     huff[i] = (uint8_t)h;
     prefix_len[i] = (uint8_t)np;
     pay_lens[i] = st == kStatusOk ? len : 0;
@@ -216,8 +224,7 @@ __global__ void hpack_finish_kernel(
         if (huff[i]) {
             const uint32_t nb = left_num[i];
             if (dec_status[i] != kStatusOk) st = dec_status[i];
-            else if (nb >= 8) st = kStatusInvalidPadding;                                 // a byte or more of padding (or EOS itself)
-            else if (nb && (left_bits[i] >> (64 - nb)) != ((1ull << nb) - 1)) st = kStatusInvalidPadding;  // not a prefix of EOS
+            else if (!hpack_padding_ok(left_bits[i], nb)) st = kStatusInvalidPadding;  // a byte or more, or not all ones
             if (st == kStatusOk) len = dec_offsets[i + 1] - dec_offsets[i];
         } else {
             len = pay_lens[i];

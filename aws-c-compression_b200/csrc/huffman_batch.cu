@@ -321,7 +321,8 @@ int encode_on_device(
 
 // Packed layout, many strings: fused count -> look-back -> write kernel (one thread per string).
 int decode_batch_fast(
-    aws_huffman_batch_ctx *ctx, Scratch &sc, const hb::BatchView &v, uint64_t total_in, cudaStream_t stream) {
+    aws_huffman_batch_ctx *ctx, Scratch &sc, const hb::BatchView &v, uint64_t total_in, cudaStream_t stream,
+    bool framed = false) {
     DecBatchArgs a{};
     a.b = v;
     a.lut = ctx->tables.lut;
@@ -359,14 +360,16 @@ int decode_batch_fast(
     a.ticket = reinterpret_cast<uint32_t *>(a.tile_state + num_tiles);
     a.num_tiles = (uint32_t)num_tiles;
     const size_t smem = lut_bytes + ((stage_bytes + 15) & ~size_t(15)) + rows_bytes + 64;
-    HB_CUDA_TRY(cudaFuncSetAttribute(decode_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HB_CUDA_TRY(cudaFuncSetAttribute(
+        framed ? decode_batch_kernel<true> : decode_batch_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned blocks = (unsigned)std::min<uint64_t>(num_tiles, (uint64_t)ctx->sm_count * 2);
     // deferred output: a block parks the dense image of a tile (never larger than its shared memory) in its own
     // slot until the next tile is decoded
     a.scratch_slot = (uint32_t)((smem + 64 + 255) & ~size_t(255));
     HB_CUDA_TRY(sc.deferred.reserve((size_t)blocks * a.scratch_slot));
     a.scratch = sc.deferred.as<uint8_t>();
-    decode_batch_kernel<<<blocks, kDecThreads, smem, stream>>>(a);
+    if (framed) decode_batch_kernel<true><<<blocks, kDecThreads, smem, stream>>>(a);
+    else decode_batch_kernel<false><<<blocks, kDecThreads, smem, stream>>>(a);
     ++ctx->launches;
     HB_CUDA_TRY(cudaGetLastError());
     return AWS_OP_SUCCESS;
@@ -851,6 +854,25 @@ int hpack_decode_on_device(
     aws_huffman_batch_ctx *ctx, uint64_t n, const uint8_t *in, const uint64_t *in_off, uint64_t total_in, uint8_t *out,
     uint64_t out_capacity, uint64_t *out_off, int32_t *status, cudaStream_t st) {
     if (n == 0) return AWS_OP_SUCCESS;
+    if (n > 1 && ctx->tables.lut_count <= kDecLutMaxSmem && !getenv("AWS_HUFFMAN_BATCH_FORCE_GENERIC") &&
+        !getenv("AWS_HUFFMAN_HPACK_PASSES")) {
+        // one kernel: the batch decoder parses the literals in its string table, copies raw payloads, applies
+        // the padding rule to what it leaves over and writes strings, offsets and status itself
+        hb::BatchView v{};
+        v.n = n;
+        v.in = in;
+        v.in_offsets = in_off;
+        v.out = out;
+        v.out_capacity = out_capacity;
+        v.out_offsets = out_off;
+        if (!status) {
+            HB_CUDA_TRY(ctx->hp_status.reserve(n * sizeof(int32_t)));
+            status = ctx->hp_status.as<int32_t>();
+        }
+        v.status = status;
+        return decode_batch_fast(ctx, ctx->scratch, v, total_in, st, true);
+    }
+    // one long literal (chunked stream kernels) or a table too large for shared memory: framing passes around the codec
     const unsigned flat = (unsigned)((n + 255) / 256), warps = (unsigned)((n + 255) / 256);  // (move kernels: 32 items per warp)
     const uint32_t min_len = std::max<uint32_t>(1, ctx->tables.min_len);
     const uint64_t dec_cap = total_in * 8 / min_len + 64;

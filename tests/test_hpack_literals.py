@@ -121,7 +121,12 @@ def test_rfc7541_literals_through_the_device(hpack_ctx):
 
 
 @pytest.mark.gpu
-def test_decode_literals_match_oracle_including_malformed(hpack_ctx, literal_oracle):
+@pytest.mark.parametrize("route", ["one_kernel", "passes"])
+def test_decode_literals_match_oracle_including_malformed(hpack_ctx, literal_oracle, monkeypatch, route):
+    """one_kernel: the batch decoder parses the literals itself (decode_batch_kernel<true>); passes: the
+    parse / gather / decode / finish / move kernels that long single literals and large tables go through."""
+    if route == "passes":
+        monkeypatch.setenv("AWS_HUFFMAN_HPACK_PASSES", "1")
     rng = np.random.default_rng(77)
     data, offs = _strings(rng, 2500, 160)
     framed, f_offs = literal_oracle.encode_batch(data, offs, lit.SMALLEST)
