@@ -19,7 +19,7 @@ tail -c 600 gpurun_out/r1/bench_hpack_batch.json
 # the widened rows: histogram and literal framing kernels
 ncu --set full --clock-control none --import-source on -k regex:"histogram_kernel" -s 3 -c 1 -o gpurun_out/r1/histogram -f \
     python tools/histogram_probe.py > /dev/null 2>&1
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"hb::" -c 200 --csv --log-file gpurun_out/r1/launches_literals.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"encode_|decode_|scan_lens|tile_index|fill_packed|hpack_" -c 200 --csv --log-file gpurun_out/r1/launches_literals.csv \
     python tools/literals_probe.py > /dev/null 2>&1
 python tools/histogram_probe.py > gpurun_out/r1/histogram.json 2>/dev/null
 python tools/literals_probe.py > gpurun_out/r1/literals.json 2>/dev/null
