@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Randomised parity run on the GPU box: random shapes through the packed encode / decode entry points against the
 oracle, for a given number of seconds. Prints the number of cases; any mismatch raises.
-    python tools/gpu_fuzz.py [seconds] [seed]"""
+    python tests/fuzz_gpu_codec.py [seconds] [seed]"""
 import os
 import sys
 import time
@@ -10,7 +10,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))  # (refcodec)
 import __graft_entry__ as graft  # noqa: E402
 import refcodec  # noqa: E402
 

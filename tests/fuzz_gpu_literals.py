@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Randomised parity run for the HPACK string-literal entry points against oracle/hpack_literals_oracle.py.
-    python tools/gpu_fuzz_literals.py [seconds] [seed]"""
+    python tests/fuzz_gpu_literals.py [seconds] [seed]"""
 import importlib.util
 import os
 import sys
