@@ -215,7 +215,9 @@ __device__ __forceinline__ uint64_t seg_resolve(uint64_t *tile_state, uint32_t t
 // tile_first[j] = first item whose start offset is >= min(j * kEncTile, total_in), for j in [0, num_tiles]
 // (so tile_first[num_tiles] is the first trailing empty item, or n)
 __global__ void tile_index_kernel(
-    const uint64_t *in_offsets, uint64_t n, uint64_t total_in, uint64_t num_tiles, uint32_t *tile_first) {
+    const uint64_t *in_offsets, uint64_t n, uint64_t total_in, uint64_t num_tiles, uint32_t *tile_first,
+    const uint32_t *gate = nullptr) {
+    if (gate != nullptr && *gate == 0) return;  // (fallback of str_pack_kernel: nothing to redo)
     const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j > num_tiles) return;
     const uint64_t target = min(j * (uint64_t)kEncTile, total_in);
@@ -240,6 +242,7 @@ struct EncTiledArgs {
     uint32_t *ticket;
     uint32_t num_tiles;
     uint32_t eos_padding;
+    const uint32_t *gate;  // not null: the launch is a fallback that only runs when *gate != 0
 };
 
 // Shared-memory table entry of the tiled encoder: x = code, y = len | len << 27 (len <= 31).
@@ -482,6 +485,7 @@ __global__ void __launch_bounds__(kEncBlock, kEncSymsPerThread == 32 ? 2 : 3) en
     const uint32_t lane = tid & 31, warp = tid >> 5;
     const uint32_t tab = tab0 + (lane & (kEncTabCopies - 1)) * 8;  // my copy of the table
 
+    if (a.gate != nullptr && *a.gate == 0) return;
     if (tid == 0) s_next = atomicAdd(a.ticket, 1u);
     if (tid < 256) {
         const uint2 e = enc_table[tid];

@@ -13,6 +13,7 @@
 #include "generic_kernels.cuh"
 #include "encode_tiled.cuh"
 #include "encode_slots.cuh"
+#include "encode_strings.cuh"
 #include "hpack_literals.cuh"
 #include "decode_fast.cuh"
 
@@ -74,10 +75,11 @@ struct GrowBuf {
 };
 // Per-launch kernel scratch (tile descriptors, chunk records, ...). One per concurrent stream.
 struct Scratch {
-    GrowBuf lens, tile_state, tile_first, chunks, chunk_lens, chunk_offsets, fused, slot_base, deferred;
+    GrowBuf lens, tile_state, tile_first, chunks, chunk_lens, chunk_offsets, fused, slot_base, deferred, str_ctl, str_state,
+        str_tiles;
     void release() {
-        GrowBuf *all[] = {&lens,          &tile_state, &tile_first,  &chunks,   &chunk_lens,
-                          &chunk_offsets, &fused,      &slot_base,   &deferred};
+        GrowBuf *all[] = {&lens,          &tile_state, &tile_first,  &chunks,   &chunk_lens, &chunk_offsets,
+                          &fused,         &slot_base,  &deferred,    &str_ctl,  &str_state,  &str_tiles};
         for (GrowBuf *g : all) g->release();
     }
 };
@@ -125,6 +127,7 @@ struct aws_huffman_batch_ctx {
     int sm_count = 148;
     int enc_blocks_per_sm[2] = {0, 0};  // resident blocks per SM of encode_tiled_kernel<seg>
     int enc_slots_blocks_per_sm = 0;
+    int str_blocks_per_sm[2] = {0, 0};  // str_measure_kernel, str_pack_kernel
     // staging for the host entry points
     GrowBuf s_in, s_in_off, s_out, s_out_off, s_caps, s_status, s_consumed, s_ovf_pattern, s_ovf_bits, s_left_bits,
         s_left_num;
@@ -132,9 +135,35 @@ struct aws_huffman_batch_ctx {
     GrowBuf hp_pay, hp_pay_off, hp_dec, hp_dec_off, hp_huff, hp_prefix, hp_lens, hp_pay_lens, hp_dec_status, hp_left_bits,
         hp_left_num, hp_status;
     uint64_t *h_scalar = nullptr;  // pinned
+    // The *_device entry points enqueue on the caller's stream but share ctx->scratch (tile descriptors, ...).
+    // `scratch_free` is recorded after every such call; a call on ANOTHER stream waits for it first, so two calls
+    // in flight on different streams never touch the scratch at the same time.
+    cudaEvent_t scratch_free = nullptr;
+    cudaStream_t scratch_stream = nullptr;
+    bool scratch_busy = false;
+    // switches, read once at context creation
+    bool force_generic = false, no_slots = false, no_strings = false, no_fused_stream = false;
 };
 
 namespace {
+
+// Stream of a *_device call: the caller's, or the context's own; ordered behind the previous device call when
+// that one ran on a different stream (they share ctx->scratch).
+int device_call_begin(aws_huffman_batch_ctx *ctx, void *cuda_stream, cudaStream_t *st) {
+    HB_CUDA_TRY(cudaSetDevice(ctx->device));
+    *st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
+    if (ctx->scratch_busy && ctx->scratch_stream != *st) HB_CUDA_TRY(cudaStreamWaitEvent(*st, ctx->scratch_free, 0));
+    return AWS_OP_SUCCESS;
+}
+int device_call_end(aws_huffman_batch_ctx *ctx, cudaStream_t st, int rc) {
+    if (ctx->scratch_free && cudaEventRecord(ctx->scratch_free, st) == cudaSuccess) {
+        ctx->scratch_stream = st;
+        ctx->scratch_busy = true;
+    } else {
+        (void)cudaGetLastError();
+    }
+    return rc;
+}
 
 constexpr uint32_t kLutRootBits = 12;
 constexpr uint32_t kLutSubBits = 8;
@@ -231,9 +260,67 @@ int encode_slots_on_device(
     return AWS_OP_SUCCESS;
 }
 
+int encode_tiled_on_device(
+    aws_huffman_batch_ctx *ctx, Scratch &sc, const hb::BatchView &v, uint64_t total_in, cudaStream_t stream,
+    const uint32_t *gate);
+
+// Packed layout, many short strings, every symbol has a code: one thread per string (encode_strings.cuh).
+int encode_strings_on_device(
+    aws_huffman_batch_ctx *ctx, Scratch &sc, const hb::BatchView &v, uint64_t total_in, cudaStream_t stream) {
+    const uint64_t measure_tiles = (v.n + kStrBatch - 1) / kStrBatch;
+    const uint32_t phase = (uint32_t)(reinterpret_cast<uintptr_t>(v.out) & 15);
+    // a symbol encodes to at most 4 bytes
+    const uint64_t cap_tiles = (4 * total_in + v.n + phase) / kStrTileBytes + 4;
+    HB_CUDA_TRY(sc.str_state.reserve(measure_tiles * sizeof(uint64_t) + 64));
+    HB_CUDA_TRY(sc.str_ctl.reserve(kStrCtlWords * sizeof(uint32_t)));
+    HB_CUDA_TRY(sc.str_tiles.reserve(cap_tiles * sizeof(uint32_t)));
+    HB_CUDA_TRY(cudaMemsetAsync(sc.str_state.ptr, 0, measure_tiles * sizeof(uint64_t), stream));
+    HB_CUDA_TRY(cudaMemsetAsync(sc.str_ctl.ptr, 0, kStrCtlWords * sizeof(uint32_t), stream));
+    HB_CUDA_TRY(cudaMemsetAsync(sc.str_tiles.ptr, 0, 16, stream));
+    StrArgs a{};
+    a.in = v.in;
+    a.in_offsets = v.in_offsets;
+    a.n = v.n;
+    a.total_in = total_in;
+    a.out = v.out;
+    a.out_capacity = v.out_capacity;
+    a.out_offsets = v.out_offsets;
+    a.tile_state = sc.str_state.as<uint64_t>();
+    a.control = sc.str_ctl.as<uint32_t>();
+    a.tile_first = sc.str_tiles.as<uint32_t>();
+    a.num_measure_tiles = (uint32_t)measure_tiles;
+    a.out_phase = phase;
+    a.eos_padding = ctx->tables.eos_padding;
+    if (!ctx->str_blocks_per_sm[0]) {
+        int per_sm = 0;
+        HB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, str_measure_kernel, kStrThreads, 0));
+        ctx->str_blocks_per_sm[0] = std::max(1, per_sm);
+        HB_CUDA_TRY(cudaFuncSetAttribute(str_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStrPackSmemBytes));
+        HB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, str_pack_kernel, kStrThreads, kStrPackSmemBytes));
+        ctx->str_blocks_per_sm[1] = std::max(1, per_sm);
+    }
+    const unsigned grid_m = (unsigned)std::min<uint64_t>(measure_tiles, (uint64_t)ctx->sm_count * ctx->str_blocks_per_sm[0]);
+    str_measure_kernel<<<grid_m, kStrThreads, 0, stream>>>(ctx->tables.enc, a);
+    const unsigned grid_p = (unsigned)std::min<uint64_t>(cap_tiles, (uint64_t)ctx->sm_count * ctx->str_blocks_per_sm[1]);
+    str_pack_kernel<<<grid_p, kStrThreads, kStrPackSmemBytes, stream>>>(ctx->tables.enc, a);
+    ctx->launches += 2;
+    HB_CUDA_TRY(cudaGetLastError());
+    // strings this path does not take (very long ones): the tiled kernel redoes the batch, on the device's own flag
+    if (encode_tiled_on_device(ctx, sc, v, total_in, stream, a.control + kStrCtlFallback)) return AWS_OP_ERR;
+    if (v.out_lens || v.status || v.consumed || v.overflow_pattern || v.overflow_num_bits) {
+        fill_packed_meta_kernel<<<(unsigned)((v.n + 255) / 256), 256, 0, stream>>>(
+            v.n, v.in_offsets, v.out_offsets, v.out_lens, v.status, v.consumed, v.overflow_pattern,
+            v.overflow_num_bits);
+        ++ctx->launches;
+        HB_CUDA_TRY(cudaGetLastError());
+    }
+    return AWS_OP_SUCCESS;
+}
+
 // Packed layout, every symbol has a code: the tiled symbol-parallel kernel.
 int encode_tiled_on_device(
-    aws_huffman_batch_ctx *ctx, Scratch &sc, const hb::BatchView &v, uint64_t total_in, cudaStream_t stream) {
+    aws_huffman_batch_ctx *ctx, Scratch &sc, const hb::BatchView &v, uint64_t total_in, cudaStream_t stream,
+    const uint32_t *gate = nullptr) {
     const uint64_t num_tiles = (total_in + kEncTile - 1) / kEncTile;
     const bool seg = v.n > 1;
     const size_t state_bytes = num_tiles * sizeof(uint64_t) + 256;
@@ -251,11 +338,12 @@ int encode_tiled_on_device(
     a.ticket = reinterpret_cast<uint32_t *>(a.tile_state + num_tiles);
     a.num_tiles = (uint32_t)num_tiles;
     a.eos_padding = ctx->tables.eos_padding;
+    a.gate = gate;
     if (seg) {
         HB_CUDA_TRY(sc.tile_first.reserve((num_tiles + 1) * sizeof(uint32_t)));
         a.tile_first = sc.tile_first.as<uint32_t>();
         tile_index_kernel<<<(unsigned)((num_tiles + 1 + 255) / 256), 256, 0, stream>>>(
-            v.in_offsets, v.n, total_in, num_tiles, sc.tile_first.as<uint32_t>());
+            v.in_offsets, v.n, total_in, num_tiles, sc.tile_first.as<uint32_t>(), gate);
         ++ctx->launches;
     }
     if (!ctx->enc_blocks_per_sm[seg]) {
@@ -279,6 +367,7 @@ int encode_tiled_on_device(
     else encode_tiled_kernel<false><<<grid, kEncBlock, kEncSmemBytes, stream>>>(ctx->tables.enc, a);
     ++ctx->launches;
     HB_CUDA_TRY(cudaGetLastError());
+    if (gate) return AWS_OP_SUCCESS;  // (the caller fills the per-item arrays once)
     if (v.out_lens || v.status || v.consumed || v.overflow_pattern || v.overflow_num_bits) {
         fill_packed_meta_kernel<<<(unsigned)((v.n + 255) / 256), 256, 0, stream>>>(
             v.n, v.in_offsets, v.out_offsets, v.out_lens, v.status, v.consumed, v.overflow_pattern,
@@ -292,13 +381,17 @@ int encode_tiled_on_device(
 int encode_on_device(
     aws_huffman_batch_ctx *ctx, Scratch &sc, hb::BatchView v, uint64_t total_in, cudaStream_t stream) {
     if (v.n == 0) return AWS_OP_SUCCESS;
-    const bool force_generic = getenv("AWS_HUFFMAN_BATCH_FORCE_GENERIC") != nullptr;
+    const bool force_generic = ctx->force_generic;
     // (the tiled kernel's multiply-add accumulator needs 1 << len to fit a word: codes of up to 31 bits)
     if (!v.resume && !v.out_caps && !ctx->tables.has_unknown && ctx->tables.max_len <= 31 && total_in > 0 && v.n < 0xffffffffull &&
         (total_in + kEncTile - 1) / kEncTile < 0xffffffffull && !force_generic) {
+        // many short strings: one thread per string
+        if (v.n > 1 && total_in / v.n <= 2048 && (reinterpret_cast<uintptr_t>(v.in) & 15) == 0 &&
+            (4 * total_in + v.n) / kStrTileBytes < 0xfffffff0ull && !ctx->no_strings)
+            return encode_strings_on_device(ctx, sc, v, total_in, stream);
         // many items of some length: thread ranges aligned to the items
         if (v.n > 1 && total_in / v.n >= 24 && total_in < (1ull << 31) && (reinterpret_cast<uintptr_t>(v.in) & 15) == 0 &&
-            !getenv("AWS_HUFFMAN_BATCH_NO_SLOTS"))
+            !ctx->no_slots)
             return encode_slots_on_device(ctx, sc, v, total_in, stream);
         return encode_tiled_on_device(ctx, sc, v, total_in, stream);
     }
@@ -409,7 +502,7 @@ int decode_stream_fast(
     const size_t fused_smem = lut_bytes + stage_bytes + (size_t)kStreamThreads * row_words * 4 + 16;
     // (the dense output image reuses the stage and the front of the rows: stream_fused_kernel step 5)
     const bool fused = (size_t)kStreamThreads * row_words * 4 + 16 <= 2 * stage_bytes - row_words * 4 - 32 &&
-                       fused_smem <= 110 * 1024 && !getenv("AWS_HUFFMAN_BATCH_NO_FUSED_STREAM");
+                       fused_smem <= 110 * 1024 && !ctx->no_fused_stream;
     if (fused) {
         StreamFusedArgs f{};
         f.s = a;
@@ -465,7 +558,7 @@ constexpr uint64_t kStreamMinBytes = 64 * 1024;  // shorter single items go thro
 int decode_on_device(
     aws_huffman_batch_ctx *ctx, Scratch &sc, hb::BatchView v, uint64_t total_in, cudaStream_t stream) {
     if (v.n == 0) return AWS_OP_SUCCESS;
-    const bool force_generic = getenv("AWS_HUFFMAN_BATCH_FORCE_GENERIC") != nullptr;
+    const bool force_generic = ctx->force_generic;
     if (!v.resume && !v.out_caps && ctx->tables.lut_count <= kDecLutMaxSmem && !force_generic) {
         if (v.n == 1 && total_in >= kStreamMinBytes) return decode_stream_fast(ctx, sc, v, total_in, stream);
         return decode_batch_fast(ctx, sc, v, total_in, stream);
@@ -526,6 +619,11 @@ int run_host_batch_pipelined(aws_huffman_batch_ctx *ctx, const aws_huffman_batch
     shards = std::min(shards, n);
     std::vector<size_t> begin(shards + 1);
     if (aws_huffman_batch_plan_shards(b->in_offsets, n, shards, begin.data())) return AWS_OP_ERR;
+    // One item larger than a sub-batch's share makes several byte targets fall inside it: plan_shards then
+    // returns empty ranges. An empty sub-batch has nothing to issue or retire (its out_offsets[0] would never
+    // be written on the device), so the ranges are compacted first.
+    begin.erase(std::unique(begin.begin(), begin.end()), begin.end());
+    shards = begin.size() - 1;
     // (cutting the first and last sub-batches smaller, to shorten pipeline fill and drain, was measured: no
     // effect — 59.5 vs 60.2 GB/s end to end)
     std::vector<uint64_t> shard_base(shards + 1, 0);
@@ -641,9 +739,20 @@ int run_host_batch_pipelined(aws_huffman_batch_ctx *ctx, const aws_huffman_batch
     // that, re-using a lane never has to wait for a D2H copy that is still running, so uploads of later
     // sub-batches and downloads of earlier ones stay concurrent.
     static_assert(hb_host::kLanes > 3, "lanes must outnumber the issue-to-retire distance");
+    // On an error no copy into the caller's buffers may still be running when the call returns.
+    auto drain = [&]() {
+        for (Lane &lane : ctx->lanes) {
+            if (lane.stream) (void)cudaStreamSynchronize(lane.stream);
+            lane.in_flight = false;
+        }
+        (void)cudaGetLastError();
+    };
     for (size_t j = 0; j < shards + depth; ++j) {
-        if (j < shards && issue(j)) return AWS_OP_ERR;
-        if (j >= depth && retire(j - depth)) return AWS_OP_ERR;
+        if ((j < shards && issue(j)) || (j >= depth && j - depth < shards && retire(j - depth))) {
+            const int err = aws_last_error();
+            drain();
+            return aws_raise_error(err ? err : AWS_ERROR_COMPRESSION_DEVICE_FAILURE);
+        }
     }
     for (Lane &lane : ctx->lanes) {
         if (lane.in_flight) HB_CUDA_TRY(cudaEventSynchronize(lane.retired));
@@ -1142,6 +1251,11 @@ static int hb_ctx_from_codes(
     if (device_id < 0 || device_id >= count) return fail(cudaErrorInvalidDevice, "device_id", __LINE__);
     HB_CTX_TRY(cudaSetDevice(device_id));
     HB_CTX_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    HB_CTX_TRY(cudaEventCreateWithFlags(&ctx->scratch_free, cudaEventDisableTiming));
+    ctx->force_generic = getenv("AWS_HUFFMAN_BATCH_FORCE_GENERIC") != nullptr;
+    ctx->no_slots = getenv("AWS_HUFFMAN_BATCH_NO_SLOTS") != nullptr;
+    ctx->no_strings = getenv("AWS_HUFFMAN_BATCH_NO_STRINGS") != nullptr;
+    ctx->no_fused_stream = getenv("AWS_HUFFMAN_BATCH_NO_FUSED_STREAM") != nullptr;
     HB_CTX_TRY(cudaMalloc(&ctx->d_enc, sizeof(enc)));
     HB_CTX_TRY(cudaMalloc(&ctx->d_lut, (size_t)lut.count * sizeof(uint32_t)));
     HB_CTX_TRY(cudaMemcpy(ctx->d_enc, enc, sizeof(enc), cudaMemcpyHostToDevice));
@@ -1205,6 +1319,7 @@ void aws_huffman_batch_ctx_destroy(struct aws_huffman_batch_ctx *ctx) {
     if (ctx->stream) {
         cudaStreamSynchronize(ctx->stream);
         cudaStreamDestroy(ctx->stream);
+        if (ctx->scratch_free) cudaEventDestroy(ctx->scratch_free);
     }
     if (ctx->d_enc) cudaFree(ctx->d_enc);
     if (ctx->d_lut) cudaFree(ctx->d_lut);
@@ -1244,11 +1359,11 @@ int aws_huffman_encode_batch_resume_device(
     void *cuda_stream) {
     if (!ctx) return aws_raise_error(AWS_ERROR_INVALID_ARGUMENT);
     if (check_batch(batch) || check_resume(batch, true)) return AWS_OP_ERR;
-    HB_CUDA_TRY(cudaSetDevice(ctx->device));
-    cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
+    cudaStream_t st;
+    if (device_call_begin(ctx, cuda_stream, &st)) return AWS_OP_ERR;
     hb::BatchView v = make_view(batch);
     v.resume = true;
-    return encode_on_device(ctx, ctx->scratch, v, batch->in_size, st);
+    return device_call_end(ctx, st, encode_on_device(ctx, ctx->scratch, v, batch->in_size, st));
 }
 
 int aws_huffman_decode_batch_resume_device(
@@ -1257,11 +1372,11 @@ int aws_huffman_decode_batch_resume_device(
     void *cuda_stream) {
     if (!ctx) return aws_raise_error(AWS_ERROR_INVALID_ARGUMENT);
     if (check_batch(batch) || check_resume(batch, false)) return AWS_OP_ERR;
-    HB_CUDA_TRY(cudaSetDevice(ctx->device));
-    cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
+    cudaStream_t st;
+    if (device_call_begin(ctx, cuda_stream, &st)) return AWS_OP_ERR;
     hb::BatchView v = make_view(batch);
     v.resume = true;
-    return decode_on_device(ctx, ctx->scratch, v, batch->in_size, st);
+    return device_call_end(ctx, st, decode_on_device(ctx, ctx->scratch, v, batch->in_size, st));
 }
 
 int aws_huffman_encode_batch_device(
@@ -1270,9 +1385,9 @@ int aws_huffman_encode_batch_device(
     void *cuda_stream) {
     if (!ctx) return aws_raise_error(AWS_ERROR_INVALID_ARGUMENT);
     if (check_batch(batch)) return AWS_OP_ERR;
-    HB_CUDA_TRY(cudaSetDevice(ctx->device));
-    cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
-    return encode_on_device(ctx, ctx->scratch, make_view(batch), batch->in_size, st);
+    cudaStream_t st;
+    if (device_call_begin(ctx, cuda_stream, &st)) return AWS_OP_ERR;
+    return device_call_end(ctx, st, encode_on_device(ctx, ctx->scratch, make_view(batch), batch->in_size, st));
 }
 
 int aws_huffman_decode_batch_device(
@@ -1281,9 +1396,9 @@ int aws_huffman_decode_batch_device(
     void *cuda_stream) {
     if (!ctx) return aws_raise_error(AWS_ERROR_INVALID_ARGUMENT);
     if (check_batch(batch)) return AWS_OP_ERR;
-    HB_CUDA_TRY(cudaSetDevice(ctx->device));
-    cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
-    return decode_on_device(ctx, ctx->scratch, make_view(batch), batch->in_size, st);
+    cudaStream_t st;
+    if (device_call_begin(ctx, cuda_stream, &st)) return AWS_OP_ERR;
+    return device_call_end(ctx, st, decode_on_device(ctx, ctx->scratch, make_view(batch), batch->in_size, st));
 }
 
 int aws_huffman_histogram_device(const uint8_t *in, uint64_t size, uint64_t *counts, void *cuda_stream) {
@@ -1336,18 +1451,20 @@ int aws_hpack_string_encode_batch_device(
     enum aws_hpack_huffman_mode mode, uint8_t *out, uint64_t out_capacity, uint64_t *out_offsets, void *cuda_stream) {
     if (!ctx || (n && (!in_offsets || !out_offsets)) || (unsigned)mode > (unsigned)AWS_HPACK_HUFFMAN_ALWAYS)
         return aws_raise_error(AWS_ERROR_INVALID_ARGUMENT);
-    HB_CUDA_TRY(cudaSetDevice(ctx->device));
-    cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
-    return hpack_encode_on_device(ctx, n, in, in_offsets, in_size, (uint32_t)mode, out, out_capacity, out_offsets, st);
+    cudaStream_t st;
+    if (device_call_begin(ctx, cuda_stream, &st)) return AWS_OP_ERR;
+    return device_call_end(
+        ctx, st, hpack_encode_on_device(ctx, n, in, in_offsets, in_size, (uint32_t)mode, out, out_capacity, out_offsets, st));
 }
 
 int aws_hpack_string_decode_batch_device(
     struct aws_huffman_batch_ctx *ctx, size_t n, const uint8_t *in, const uint64_t *in_offsets, uint64_t in_size,
     uint8_t *out, uint64_t out_capacity, uint64_t *out_offsets, int32_t *status, void *cuda_stream) {
     if (!ctx || (n && (!in_offsets || !out_offsets))) return aws_raise_error(AWS_ERROR_INVALID_ARGUMENT);
-    HB_CUDA_TRY(cudaSetDevice(ctx->device));
-    cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
-    return hpack_decode_on_device(ctx, n, in, in_offsets, in_size, out, out_capacity, out_offsets, status, st);
+    cudaStream_t st;
+    if (device_call_begin(ctx, cuda_stream, &st)) return AWS_OP_ERR;
+    return device_call_end(
+        ctx, st, hpack_decode_on_device(ctx, n, in, in_offsets, in_size, out, out_capacity, out_offsets, status, st));
 }
 
 int aws_huffman_get_encoded_length_batch(
