@@ -4,8 +4,10 @@
 // huffman.c:178-184), so the only thing an item needs from the others is a BYTE offset. That splits the
 // work into
 //
-//   str_measure_kernel   encoded length of every string (huffman.c:107-129: sum of code lengths, rounded up
-//                        to bytes), block scan + single-pass decoupled look-back -> out_offsets[0..n];
+//   str_bits_kernel      code-length sums (huffman.c:107-129) over FLAT 16 KiB tiles of the input, prefix sums
+//                        left in shared memory; a string's bits are two look-ups (str_prep_kernel zeroes
+//                        the scratch and finds each flat tile's first string)
+//   str_scan_kernel      bits -> bytes, block scan + single-pass decoupled look-back -> out_offsets[0..n];
 //                        also cuts the OUTPUT into tiles of kStrTileBytes (tile k = the strings that start
 //                        in output bytes [kT, (k+1)T)) and records each tile's first string
 //   str_pack_kernel      per output tile: every thread packs whole strings with the carry-flag append of
@@ -39,10 +41,10 @@ namespace hb {
 #define HB_STR_TILE_BYTES (40 * 1024)
 #endif
 #ifndef HB_STR_TAB_COPIES
-#define HB_STR_TAB_COPIES 8
+#define HB_STR_TAB_COPIES 16
 #endif
 #ifndef HB_STR_PACK_BLOCKS
-#define HB_STR_PACK_BLOCKS 3
+#define HB_STR_PACK_BLOCKS 2
 #endif
 
 constexpr int kStrThreads = 256;
@@ -57,7 +59,7 @@ constexpr uint32_t kStrTabStride = 8 * kStrTabCopies;        // bytes between en
 constexpr uint32_t kStrTabBytes = 257 * kStrTabStride;       // entry 256 = {0, 0}: "no symbol"
 static_assert(kStrTileBytes % 16 == 0, "tiles start on 16-byte boundaries of the output");
 
-// control block (device memory, zeroed before str_measure_kernel)
+// control block (device memory, zeroed by str_prep_kernel)
 enum : int { kStrCtlTicket = 0, kStrCtlFallback = 1, kStrCtlNumTiles = 2, kStrCtlWords = 8 };
 
 struct StrArgs {
@@ -67,8 +69,8 @@ struct StrArgs {
     uint64_t total_in;
     uint8_t *out;
     uint64_t out_capacity;
-    uint64_t *out_offsets;       // n + 1, written by str_measure_kernel
-    uint64_t *tile_state;        // look-back descriptors of str_measure_kernel (32-byte aligned, zeroed)
+    uint64_t *out_offsets;       // n + 1, written by str_scan_kernel
+    uint64_t *tile_state;        // look-back descriptors of str_scan_kernel (32-byte aligned, zeroed by str_prep_kernel)
     uint32_t *control;           // kStrCtlWords words, zeroed
     uint32_t *tile_first;        // output tiles: first string of tile k; [0] zeroed
     uint32_t num_measure_tiles;
@@ -138,133 +140,253 @@ __device__ __forceinline__ uint32_t str_word(const uint4 &v, int k) {
 }
 
 // ---- measure ------------------------------------------------------------------------------------------------
-struct StrMeasure {
-    uint32_t bits;
-    uint32_t tab;  // shared-window address of the 256-byte code length table
-    __device__ __forceinline__ uint32_t len_of(uint32_t word, int k) const {
-        const uint32_t byte = __byte_perm(word, 0, 0x4440 | (k & 3));
-        uint32_t l;
-        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(l) : "r"(tab + byte));
-        return l;
-    }
-    __device__ __forceinline__ void full(const uint4 &v) {
-        uint32_t s0 = 0, s1 = 0;
-#pragma unroll
-        for (int k = 0; k < 16; k += 2) {
-            s0 += len_of(str_word(v, k), k);
-            s1 += len_of(str_word(v, k + 1), k + 1);
-        }
-        bits += s0 + s1;
-    }
-    __device__ __forceinline__ void masked(const uint4 &v, uint32_t lo, uint32_t hi) {
-        const uint32_t width = hi - lo;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const uint32_t l = len_of(str_word(v, k), k);
-            bits += ((uint32_t)k - lo < width) ? l : 0u;
-        }
-    }
+// The encoded length of a string is a plain SUM over its bytes, so the measuring does not have to follow the
+// strings: the input is cut into flat tiles of kBitsTileBytes, every thread sums whole aligned 16-byte
+// vectors (coalesced 128-bit loads, no sorting, no partial vectors, every lane busy) and leaves the running
+// sums behind in shared memory — per vector the inclusive prefix after each of its 16 bytes (u16), per tile the
+// exclusive prefix over its vectors. The bits of a string are then cum(end) - cum(start), two look-ups; a
+// string that crosses tiles collects its pieces with atomicAdd. (First version: one thread per string with
+// the sorted walk of the pack kernel: 89 us for 1M strings; this one: see profiles/README.md.)
+constexpr int kBitsThreads = 256;
+constexpr int kBitsVecsPerThread = 4;
+constexpr int kBitsTileVecs = kBitsThreads * kBitsVecsPerThread;  // 1024
+constexpr uint32_t kBitsTileBytes = 16u * kBitsTileVecs;          // 16 KiB of input per tile
+
+struct StrPrepArgs {
+    const uint64_t *in_offsets;
+    uint64_t n, total_in;
+    uint32_t *bits;             // n (rounded up to 4) words, zeroed here
+    uint32_t *bits_tile_first;  // num_bits_tiles + 1: first string that starts at or after the tile's first byte
+    uint64_t *tile_state;       // num_scan_tiles descriptors, zeroed here
+    uint32_t *control;          // zeroed here
+    uint32_t *tile_first;       // [0] zeroed here
+    uint32_t num_bits_tiles, num_scan_tiles;
 };
 
-__global__ void __launch_bounds__(kStrThreads, 4) str_measure_kernel(const uint2 *__restrict__ enc_table, StrArgs a) {
-    __shared__ __align__(16) uint8_t s_lentab[256];
-    __shared__ uint32_t s_inrel[kStrBatch];
-    __shared__ uint32_t s_len[kStrBatch];
-    __shared__ uint32_t s_bytes[kStrBatch];
-    __shared__ uint16_t s_perm[kStrBatch];
-    __shared__ uint32_t s_hist[kStrThreads];
-    __shared__ uint32_t s_wsum[kStrWarps];
-    __shared__ uint32_t s_tile;
-    __shared__ uint64_t s_prefix;
+// One launch instead of three memsets and an index kernel. The flat tiles' first strings are SCATTERED by the
+// strings themselves (string i opens every tile whose first byte lies in (in_offsets[i-1], in_offsets[i]]): one
+// coalesced pass over the offsets instead of a 20-step binary search per tile (12 us of dependent loads).
+__global__ void str_prep_kernel(StrPrepArgs a) {
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = g; i < a.num_scan_tiles; i += stride) a.tile_state[i] = 0;
+    if (g < kStrCtlWords) a.control[g] = 0;
+    if (g == 0) a.tile_first[0] = 0;
+    for (uint64_t i = g; i <= a.n; i += stride) {
+        if (i < a.n) a.bits[i] = 0;
+        const uint64_t cur = a.in_offsets[i];
+        // tiles j with prev < j * T <= cur (prev = "-1" for the first string)
+        uint64_t j = i ? a.in_offsets[i - 1] / kBitsTileBytes + 1 : 0;
+        const bool last = (i == 0 || a.in_offsets[i - 1] < a.total_in) && a.total_in <= cur;
+        for (; j * kBitsTileBytes <= cur && j < a.num_bits_tiles; ++j) a.bits_tile_first[j] = (uint32_t)i;
+        if (last) a.bits_tile_first[a.num_bits_tiles] = (uint32_t)i;
+    }
+}
 
+struct StrBitsArgs {
+    const uint8_t *in;  // 16-byte aligned
+    const uint64_t *in_offsets;
+    uint64_t n, total_in;
+    const uint32_t *bits_tile_first;
+    uint32_t *bits;
+    uint32_t *control;
+    uint32_t num_bits_tiles;
+};
+
+__global__ void __launch_bounds__(kBitsThreads, 4) str_bits_kernel(const uint2 *__restrict__ enc_table, StrBitsArgs a) {
+    __shared__ __align__(16) uint8_t s_lentab[256];
+    __shared__ __align__(16) uint32_t s_pre[kBitsTileVecs][8];  // per vector: inclusive prefix after byte 2j | after byte 2j+1 << 16
+    __shared__ uint32_t s_vex[kBitsTileVecs + 1];               // exclusive prefix over the vectors; [nvec] = the tile's total
+    __shared__ uint32_t s_wsum[kBitsThreads / 32];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     s_lentab[tid] = (uint8_t)enc_table[tid].y;
-    const uint8_t *const in_end = a.in + a.total_in;
-    StrMeasure m;
-    m.tab = smem_addr(s_lentab);
+    const uint32_t tab = smem_addr(s_lentab);
 
-    for (;;) {
-        __syncthreads();  // previous tile done with the shared arrays (first trip: the table is in place)
-        if (tid == 0) s_tile = atomicAdd(&a.control[kStrCtlTicket], 1u);
-        __syncthreads();
-        const uint32_t tile = s_tile;
-        if (tile >= a.num_measure_tiles) break;
-        const uint64_t item0 = (uint64_t)tile * kStrBatch;
-        const uint32_t cnt = (uint32_t)min((uint64_t)kStrBatch, a.n - item0);
-        const uint64_t base0 = a.in_offsets[item0];
-        bool wide = false;
+    // bits of the tile's bytes [0, x)
+    auto cum = [&](uint32_t x) -> uint32_t {
+        const uint32_t v = x >> 4, k = x & 15u;
+        uint32_t c = s_vex[v];
+        if (k) {
+            const uint32_t w = s_pre[v][(k - 1) >> 1];
+            c += ((k - 1) & 1u) ? w >> 16 : w & 0xffffu;
+        }
+        return c;
+    };
+
+    for (uint32_t tile = blockIdx.x; tile < a.num_bits_tiles; tile += gridDim.x) {
+        const uint64_t t0 = (uint64_t)tile * kBitsTileBytes;
+        const uint32_t tile_len = (uint32_t)min((uint64_t)kBitsTileBytes, a.total_in - t0);
+        const uint32_t nvec = (tile_len + 15u) >> 4;
+        const uint4 *vp = reinterpret_cast<const uint4 *>(a.in + t0);
+        __syncthreads();  // the previous tile's look-ups are over (first trip: the table is in place)
+        uint4 v[kBitsVecsPerThread];
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const uint32_t idx = tid + q * kStrThreads;
-            if (idx < cnt) {
-                const uint64_t o0 = a.in_offsets[item0 + idx], o1 = a.in_offsets[item0 + idx + 1];
-                // (a string this path does not take is measured as empty: the flag sends the batch elsewhere)
-                const bool big = (o1 - base0) >= (1ull << 32) || (o1 - o0) > kStrMaxInput;
-                wide |= big;
-                s_inrel[idx] = big ? 0u : (uint32_t)(o0 - base0);
-                s_len[idx] = big ? 0u : (uint32_t)(o1 - o0);
+        for (int i = 0; i < kBitsVecsPerThread; ++i) {
+            const uint32_t vi = i * kBitsThreads + tid;
+            v[i] = make_uint4(0, 0, 0, 0);
+            if (16u * vi + 16u <= tile_len) {
+                v[i] = __ldg(vp + vi);
+            } else if (vi < nvec) {  // the input's last, partial vector
+                uint32_t w[4] = {0, 0, 0, 0};
+                for (uint32_t b = 0; 16u * vi + b < tile_len; ++b) w[b >> 2] |= (uint32_t)a.in[t0 + 16u * vi + b] << (8 * (b & 3));
+                v[i] = make_uint4(w[0], w[1], w[2], w[3]);
             }
         }
-        if (wide) atomicOr(&a.control[kStrCtlFallback], 1u);
-        str_sort(s_len, cnt, s_perm, s_hist, s_wsum);
-        // zigzag: the tid-th longest, then the tid-th shortest of the 512
-#pragma unroll 1
-        for (int q = 0; q < 2; ++q) {
-            const uint32_t pos = q == 0 ? tid : (uint32_t)kStrBatch - 1u - tid;
-            if (pos < cnt) {
-                const uint32_t idx = s_perm[pos];
-                m.bits = 0;
-                str_walk(a.in + base0 + s_inrel[idx], s_len[idx], in_end, m);
-                s_bytes[idx] = (m.bits + 7u) >> 3;
+        uint32_t tot[kBitsVecsPerThread];
+#pragma unroll
+        for (int i = 0; i < kBitsVecsPerThread; ++i) {
+            const uint32_t vi = i * kBitsThreads + tid;
+            uint32_t run = 0, pk[8];
+#pragma unroll
+            for (int k = 0; k < 16; k += 2) {
+                const uint32_t w = str_word(v[i], k);
+                uint32_t l0, l1;
+                asm volatile("ld.shared.u8 %0, [%1];" : "=r"(l0) : "r"(tab + __byte_perm(w, 0, 0x4440 | (k & 3))));
+                asm volatile("ld.shared.u8 %0, [%1];" : "=r"(l1) : "r"(tab + __byte_perm(w, 0, 0x4440 | ((k + 1) & 3))));
+                const uint32_t p0 = run + l0;
+                run = p0 + l1;
+                pk[k >> 1] = p0 | (run << 16);
             }
+            *reinterpret_cast<uint4 *>(&s_pre[vi][0]) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4 *>(&s_pre[vi][4]) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            tot[i] = run;
+            s_vex[vi] = run;  // (raw totals first; scanned below)
         }
         __syncthreads();
-        // block scan in item order, two items per thread
-        const uint32_t b0 = 2 * tid < cnt ? s_bytes[2 * tid] : 0u;
-        const uint32_t b1 = 2 * tid + 1 < cnt ? s_bytes[2 * tid + 1] : 0u;
-        const uint32_t incl = warp_inclusive_scan(b0 + b1);
+        // exclusive scan over the vectors in order: four consecutive vectors per thread
+        uint32_t q[4], sum = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            q[j] = s_vex[4 * tid + j];
+            sum += q[j];
+        }
+        const uint32_t incl = warp_inclusive_scan(sum);
         if (lane == 31) s_wsum[warp] = incl;
         __syncthreads();
-        uint32_t before = 0, total = 0;
+        uint32_t run = incl - sum;
 #pragma unroll
-        for (int w = 0; w < kStrWarps; ++w) {
-            const uint32_t ws = s_wsum[w];
-            if ((uint32_t)w < warp) before += ws;
-            total += ws;
+        for (int w = 0; w < kBitsThreads / 32; ++w)
+            if ((uint32_t)w < warp) run += s_wsum[w];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            s_vex[4 * tid + j] = run;
+            run += q[j];
         }
-        if (tid == 0) lookback_publish_aggregate(a.tile_state, tile, total);
-        if (warp == 0) {
-            const uint64_t prefix = lookback_resolve(a.tile_state, tile, total);
-            if (lane == 0) s_prefix = prefix;
-        }
+        if (tid == kBitsThreads - 1) s_vex[kBitsTileVecs] = run;
         __syncthreads();
-        const uint64_t prefix = s_prefix;
-        uint64_t o = prefix + before + incl - (b0 + b1);
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const uint32_t idx = 2 * tid + q;
-            const uint32_t bytes = q == 0 ? b0 : b1;
-            if (idx < cnt) {
-                const uint64_t item = item0 + idx;
-                a.out_offsets[item] = o;
-                if (bytes > kStrSlackBytes) atomicOr(&a.control[kStrCtlFallback], 1u);
-                // output tiles: the next string opens tile k1 when this one crosses into it
-                const uint64_t k0 = (o + a.out_phase) / kStrTileBytes, k1 = (o + bytes + a.out_phase) / kStrTileBytes;
-                if (a.tile_first && bytes <= kStrSlackBytes) {
-                    if (k1 != k0) a.tile_first[k1] = (uint32_t)(item + 1);
-                    if (item + 1 == a.n) {
-                        a.tile_first[k1 + 1] = (uint32_t)a.n;
-                        a.control[kStrCtlNumTiles] = (uint32_t)(k1 + 1);
-                    }
-                }
-                if (item + 1 == a.n) a.out_offsets[a.n] = o + bytes;
-            }
-            o += bytes;
+        (void)tot;
+        // the strings that start in this tile, and the one that continues into it
+        const uint32_t f0 = a.bits_tile_first[tile], f1 = a.bits_tile_first[tile + 1];
+        if (tid == 0 && f0 > 0) {
+            const uint64_t endc = a.in_offsets[f0];
+            if (endc > t0) atomicAdd(&a.bits[f0 - 1], cum((uint32_t)min(endc - t0, (uint64_t)tile_len)));
+        }
+        for (uint32_t i = f0 + tid; i < f1; i += kBitsThreads) {
+            const uint64_t s = a.in_offsets[i] - t0, e = a.in_offsets[i + 1] - t0;
+            if (e - s > kStrMaxInput) atomicOr(&a.control[kStrCtlFallback], 1u);  // (its bit count may not fit 32 bits)
+            if (e <= tile_len) a.bits[i] = cum((uint32_t)e) - cum((uint32_t)s);
+            else atomicAdd(&a.bits[i], cum(tile_len) - cum((uint32_t)s));
         }
     }
 }
 
+// bits -> bytes -> out_offsets (block scan + single-pass decoupled look-back), the output tiles of
+// str_pack_kernel, and the flag that sends batches with strings it does not take to the tiled kernel.
+constexpr int kStrScanPerThread = 8;
+constexpr int kStrScanTile = kStrThreads * kStrScanPerThread;  // 2048 strings per block
+
+__global__ void __launch_bounds__(kStrThreads) str_scan_kernel(const uint32_t *__restrict__ bits, StrArgs a) {
+    __shared__ uint32_t s_wsum[kStrWarps];
+    __shared__ uint32_t s_tile;
+    __shared__ uint64_t s_prefix;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(&a.control[kStrCtlTicket], 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint64_t item0 = (uint64_t)tile * kStrScanTile + (uint64_t)kStrScanPerThread * tid;
+    uint32_t by[kStrScanPerThread];
+    uint32_t sum = 0;
+    bool big = false;
+    if (item0 + kStrScanPerThread <= a.n) {  // (the scratch is 16-byte aligned and a multiple of 8 strings from it)
+        const uint4 lo = *reinterpret_cast<const uint4 *>(bits + item0), hi = *reinterpret_cast<const uint4 *>(bits + item0 + 4);
+        by[0] = lo.x; by[1] = lo.y; by[2] = lo.z; by[3] = lo.w; by[4] = hi.x; by[5] = hi.y; by[6] = hi.z; by[7] = hi.w;
+    } else {
+#pragma unroll
+        for (int q = 0; q < kStrScanPerThread; ++q) by[q] = item0 + q < a.n ? bits[item0 + q] : 0u;
+    }
+#pragma unroll
+    for (int q = 0; q < kStrScanPerThread; ++q) {
+        by[q] = (by[q] + 7u) >> 3;
+        big |= by[q] > kStrSlackBytes;
+        sum += by[q];
+    }
+    if (big) atomicOr(&a.control[kStrCtlFallback], 1u);
+    const uint32_t incl = warp_inclusive_scan(sum);
+    if (lane == 31) s_wsum[warp] = incl;
+    __syncthreads();
+    uint32_t before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kStrWarps; ++w) {
+        const uint32_t ws = s_wsum[w];
+        if ((uint32_t)w < warp) before += ws;
+        total += ws;
+    }
+    if (tid == 0) lookback_publish_aggregate(a.tile_state, tile, total);
+    if (warp == 0) {
+        const uint64_t prefix = lookback_resolve(a.tile_state, tile, total);
+        if (lane == 0) s_prefix = prefix;
+    }
+    __syncthreads();
+    uint64_t o = s_prefix + before + incl - sum;
+#pragma unroll
+    for (int q = 0; q < kStrScanPerThread; ++q) {
+        const uint64_t item = item0 + q;
+        const uint32_t bytes = by[q];
+        if (item < a.n) {
+            a.out_offsets[item] = o;
+            // output tiles: the next string opens tile k1 when this one crosses into it
+            const uint64_t k0 = (o + a.out_phase) / kStrTileBytes, k1 = (o + bytes + a.out_phase) / kStrTileBytes;
+            if (bytes <= kStrSlackBytes) {
+                if (k1 != k0) a.tile_first[k1] = (uint32_t)(item + 1);
+                if (item + 1 == a.n) {
+                    a.tile_first[k1 + 1] = (uint32_t)a.n;
+                    a.control[kStrCtlNumTiles] = (uint32_t)(k1 + 1);
+                }
+            }
+            if (item + 1 == a.n) a.out_offsets[a.n] = o + bytes;
+        }
+        o += bytes;
+    }
+}
+
 // ---- pack ---------------------------------------------------------------------------------------------------
+// enc_append of encode_tiled.cuh without the store pointer: the low field of the bit counter holds the ABSOLUTE
+// bit address in the shared window (8 * byte address + bit), so the word that a carry completes lies at
+// ((nb >> 3) & ~3) - 4. A pointer that is bumped right behind the predicated store it addresses makes the warp
+// wait until the store has read its operands (measured: a third of the stall samples of the packing loop sat
+// on that add); a fresh temporary per symbol has no such dependency.
+#ifndef HB_STR_PTR_APPEND
+#define HB_STR_PTR_APPEND 0
+#endif
+__device__ __forceinline__ void str_append(uint32_t &acc, uint32_t &nb, uint32_t code, uint32_t ey) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b32 pw, hi, t;\n\t"
+        "shf.l.wrap.b32 pw, 0, 1, %2;\n\t"
+        "mul.hi.u32 hi, %0, pw;\n\t"
+        "mad.lo.u32 %0, %0, pw, %3;\n\t"
+        "add.u32 %1, %1, %2;\n\t"
+        "setp.lt.u32 p, %1, %2;\n\t"
+        "shf.r.wrap.b32 hi, %0, hi, %1;\n\t"
+        "shr.u32 t, %1, 3;\n\t"
+        "and.b32 t, t, 0x00fffffc;\n\t"
+        "@p st.shared.u32 [t+-4], hi;\n\t"
+        "}"
+        : "+r"(acc), "+r"(nb)
+        : "r"(ey), "r"(code)
+        : "memory");
+}
+
 struct StrPack {
     uint32_t sp, acc, nb;
     uint32_t tab;   // shared-window address of MY copy's entry 0
@@ -286,7 +408,31 @@ struct StrPack {
 #pragma unroll
         for (int k = 0; k < 16; ++k) e[k] = fetch(entry(str_word(v, k), k));
 #pragma unroll
-        for (int k = 0; k < 16; ++k) enc_append(sp, acc, nb, e[k].x, e[k].y);
+        for (int k = 0; k < 16; ++k) put(e[k].x, e[k].y);
+    }
+    __device__ __forceinline__ void put(uint32_t code, uint32_t ey) {
+#if HB_STR_PTR_APPEND
+        enc_append(sp, acc, nb, code, ey);
+#else
+        str_append(acc, nb, code, ey);
+#endif
+    }
+    // where the next completed word goes / how many bits of it are there
+    __device__ __forceinline__ void start(uint32_t word_addr, uint32_t lead_bits, uint32_t lead_value) {
+        acc = lead_value;
+#if HB_STR_PTR_APPEND
+        sp = word_addr;
+        nb = enc_len_fields(lead_bits);
+#else
+        nb = (lead_bits << 27) | (8u * word_addr + lead_bits);
+#endif
+    }
+    __device__ __forceinline__ uint32_t word_addr() const {
+#if HB_STR_PTR_APPEND
+        return sp;
+#else
+        return (nb >> 3) & 0x00fffffcu;
+#endif
     }
     __device__ __forceinline__ void masked(const uint4 &v, uint32_t lo, uint32_t hi) {
         const uint32_t width = hi - lo;
@@ -297,7 +443,7 @@ struct StrPack {
             e[k] = fetch(((uint32_t)k - lo < width) ? addr : zero);
         }
 #pragma unroll
-        for (int k = 0; k < 16; ++k) enc_append(sp, acc, nb, e[k].x, e[k].y);
+        for (int k = 0; k < 16; ++k) put(e[k].x, e[k].y);
     }
 };
 
@@ -371,18 +517,17 @@ __global__ void __launch_bounds__(kStrThreads, HB_STR_PACK_BLOCKS) str_pack_kern
                     const uint32_t idx = s_perm[pos];
                     const uint32_t orel = s_orel[idx];
                     const uint32_t lead = 8u * (orel & 3u);  // bits of my first word that belong to earlier strings
-                    pk.sp = stage_addr + (orel & ~3u);
+                    const uint32_t w0 = stage_addr + (orel & ~3u);
                     uint32_t first;
-                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(first) : "r"(pk.sp));
-                    pk.acc = lead ? first >> (32u - lead) : 0u;
-                    pk.nb = enc_len_fields(lead);
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(first) : "r"(w0));
+                    pk.start(w0, lead, lead ? first >> (32u - lead) : 0u);
                     str_walk(a.in + base0 + s_inrel[idx], s_len[idx], in_end, pk);
                     // pad the last byte with the LOW bits of eos_padding (huffman.c:178-184)
                     const uint32_t pad = (0u - pk.nb) & 7u;
-                    enc_append(pk.sp, pk.acc, pk.nb, a.eos_padding & ((1u << pad) - 1u), enc_len_fields(pad));
+                    pk.put(a.eos_padding & ((1u << pad) - 1u), enc_len_fields(pad));
                     const uint32_t rem = pk.nb >> 27;
                     if (rem) {
-                        tail_addr[q] = pk.sp;
+                        tail_addr[q] = pk.word_addr();
                         tail_word[q] = pk.acc << (32u - rem);
                     }
                 }

@@ -76,10 +76,11 @@ struct GrowBuf {
 // Per-launch kernel scratch (tile descriptors, chunk records, ...). One per concurrent stream.
 struct Scratch {
     GrowBuf lens, tile_state, tile_first, chunks, chunk_lens, chunk_offsets, fused, slot_base, deferred, str_ctl, str_state,
-        str_tiles;
+        str_tiles, str_bits, str_bits_first;
     void release() {
         GrowBuf *all[] = {&lens,          &tile_state, &tile_first,  &chunks,   &chunk_lens, &chunk_offsets,
-                          &fused,         &slot_base,  &deferred,    &str_ctl,  &str_state,  &str_tiles};
+                          &fused,         &slot_base,  &deferred,    &str_ctl,  &str_state,  &str_tiles,
+                          &str_bits,      &str_bits_first};
         for (GrowBuf *g : all) g->release();
     }
 };
@@ -127,7 +128,7 @@ struct aws_huffman_batch_ctx {
     int sm_count = 148;
     int enc_blocks_per_sm[2] = {0, 0};  // resident blocks per SM of encode_tiled_kernel<seg>
     int enc_slots_blocks_per_sm = 0;
-    int str_blocks_per_sm[2] = {0, 0};  // str_measure_kernel, str_pack_kernel
+    int str_blocks_per_sm[3] = {0, 0, 0};  // str_bits_kernel, str_pack_kernel, str_scan_kernel
     // staging for the host entry points
     GrowBuf s_in, s_in_off, s_out, s_out_off, s_caps, s_status, s_consumed, s_ovf_pattern, s_ovf_bits, s_left_bits,
         s_left_num;
@@ -267,16 +268,16 @@ int encode_tiled_on_device(
 // Packed layout, many short strings, every symbol has a code: one thread per string (encode_strings.cuh).
 int encode_strings_on_device(
     aws_huffman_batch_ctx *ctx, Scratch &sc, const hb::BatchView &v, uint64_t total_in, cudaStream_t stream) {
-    const uint64_t measure_tiles = (v.n + kStrBatch - 1) / kStrBatch;
+    const uint64_t scan_tiles = (v.n + kStrScanTile - 1) / kStrScanTile;
+    const uint64_t bits_tiles = (total_in + kBitsTileBytes - 1) / kBitsTileBytes;
     const uint32_t phase = (uint32_t)(reinterpret_cast<uintptr_t>(v.out) & 15);
     // a symbol encodes to at most 4 bytes
     const uint64_t cap_tiles = (4 * total_in + v.n + phase) / kStrTileBytes + 4;
-    HB_CUDA_TRY(sc.str_state.reserve(measure_tiles * sizeof(uint64_t) + 64));
+    HB_CUDA_TRY(sc.str_state.reserve(scan_tiles * sizeof(uint64_t) + 64));
     HB_CUDA_TRY(sc.str_ctl.reserve(kStrCtlWords * sizeof(uint32_t)));
     HB_CUDA_TRY(sc.str_tiles.reserve(cap_tiles * sizeof(uint32_t)));
-    HB_CUDA_TRY(cudaMemsetAsync(sc.str_state.ptr, 0, measure_tiles * sizeof(uint64_t), stream));
-    HB_CUDA_TRY(cudaMemsetAsync(sc.str_ctl.ptr, 0, kStrCtlWords * sizeof(uint32_t), stream));
-    HB_CUDA_TRY(cudaMemsetAsync(sc.str_tiles.ptr, 0, 16, stream));
+    HB_CUDA_TRY(sc.str_bits.reserve((v.n + 8) * sizeof(uint32_t)));
+    HB_CUDA_TRY(sc.str_bits_first.reserve((bits_tiles + 1) * sizeof(uint32_t)));
     StrArgs a{};
     a.in = v.in;
     a.in_offsets = v.in_offsets;
@@ -288,22 +289,46 @@ int encode_strings_on_device(
     a.tile_state = sc.str_state.as<uint64_t>();
     a.control = sc.str_ctl.as<uint32_t>();
     a.tile_first = sc.str_tiles.as<uint32_t>();
-    a.num_measure_tiles = (uint32_t)measure_tiles;
+    a.num_measure_tiles = (uint32_t)scan_tiles;
     a.out_phase = phase;
     a.eos_padding = ctx->tables.eos_padding;
+    StrPrepArgs p{};
+    p.in_offsets = v.in_offsets;
+    p.n = v.n;
+    p.total_in = total_in;
+    p.bits = sc.str_bits.as<uint32_t>();
+    p.bits_tile_first = sc.str_bits_first.as<uint32_t>();
+    p.tile_state = a.tile_state;
+    p.control = a.control;
+    p.tile_first = a.tile_first;
+    p.num_bits_tiles = (uint32_t)bits_tiles;
+    p.num_scan_tiles = (uint32_t)scan_tiles;
+    StrBitsArgs m{};
+    m.in = v.in;
+    m.in_offsets = v.in_offsets;
+    m.n = v.n;
+    m.total_in = total_in;
+    m.bits_tile_first = p.bits_tile_first;
+    m.bits = p.bits;
+    m.control = a.control;
+    m.num_bits_tiles = (uint32_t)bits_tiles;
     if (!ctx->str_blocks_per_sm[0]) {
         int per_sm = 0;
-        HB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, str_measure_kernel, kStrThreads, 0));
+        HB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, str_bits_kernel, kBitsThreads, 0));
         ctx->str_blocks_per_sm[0] = std::max(1, per_sm);
         HB_CUDA_TRY(cudaFuncSetAttribute(str_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStrPackSmemBytes));
         HB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, str_pack_kernel, kStrThreads, kStrPackSmemBytes));
         ctx->str_blocks_per_sm[1] = std::max(1, per_sm);
     }
-    const unsigned grid_m = (unsigned)std::min<uint64_t>(measure_tiles, (uint64_t)ctx->sm_count * ctx->str_blocks_per_sm[0]);
-    str_measure_kernel<<<grid_m, kStrThreads, 0, stream>>>(ctx->tables.enc, a);
+    const unsigned grid_prep = (unsigned)std::min<uint64_t>((v.n + 256) / 256, (uint64_t)ctx->sm_count * 16);
+    str_prep_kernel<<<grid_prep, 256, 0, stream>>>(p);
+    const unsigned grid_b = (unsigned)std::min<uint64_t>(std::max<uint64_t>(1, bits_tiles), (uint64_t)ctx->sm_count * ctx->str_blocks_per_sm[0]);
+    str_bits_kernel<<<grid_b, kBitsThreads, 0, stream>>>(ctx->tables.enc, m);
+    const unsigned grid_s = (unsigned)scan_tiles;
+    str_scan_kernel<<<grid_s, kStrThreads, 0, stream>>>(p.bits, a);
     const unsigned grid_p = (unsigned)std::min<uint64_t>(cap_tiles, (uint64_t)ctx->sm_count * ctx->str_blocks_per_sm[1]);
     str_pack_kernel<<<grid_p, kStrThreads, kStrPackSmemBytes, stream>>>(ctx->tables.enc, a);
-    ctx->launches += 2;
+    ctx->launches += 4;
     HB_CUDA_TRY(cudaGetLastError());
     // strings this path does not take (very long ones): the tiled kernel redoes the batch, on the device's own flag
     if (encode_tiled_on_device(ctx, sc, v, total_in, stream, a.control + kStrCtlFallback)) return AWS_OP_ERR;

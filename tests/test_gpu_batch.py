@@ -466,7 +466,7 @@ def test_zero_copy_host_path(contexts, oracle, oracle_tables, pkg, shape, monkey
     launches = ctx.launch_count
     out = _pinned(np.full(cap, 0xA5, dtype=np.uint8))
     got = ctx.encode(_pinned(data), offs, cap, out=out)
-    assert ctx.launch_count - launches <= 6, "one pass of kernels over the caller's buffers, no sub-batches"
+    assert ctx.launch_count - launches <= 8, "one pass of kernels over the caller's buffers, no sub-batches"
     assert_same_packed(got, want)
     assert (got["out"][total:] == 0xA5).all(), "bytes after the result were touched"
 
