@@ -567,18 +567,288 @@ __device__ __forceinline__ SpanS decode_span_smem(
 }
 
 // ---------------------------------------------------------------------------------------------
+// The LEAN decode step (round 2): the same walk over the same tables, re-encoded as 64-bit entries ("LUT2",
+// built in huffman_batch.cu from the 32-bit LUT) so that a step needs no selects and no per-table state
+// machine:
+//     x  [7:0] symbol 1   [15:8] symbol 2   [21:16] length of symbol 1's code from the symbol's first bit
+//        [31:30] symbols in the entry (0: link or hole)
+//     y  [31:24] bits this step consumes   [23:5] shared-memory address of the table the NEXT step indexes
+//        (32-byte aligned)   [4:0] 32 - index width of that table
+// A leaf sends the lane back to the root table, a link to its sub-table — after consuming the index bits of the
+// level it was found in, so the next step indexes the sub-table with the bits that follow (sub-table leaves
+// consume what is left of the code). Whatever the entry is, a step is: funnel, shift by y (the hardware takes
+// the low five bits), one multiply-add for the address, one 64-bit load, `pos += y >> 24`, two byte stores,
+// `out += x >> 30`, the cursor refill. 20 instructions against 37 of the unified step of round 1.
+// A hole (no code matches) leads to a trap table whose entries consume nothing; trapped lanes are noticed
+// once per round and the whole span is then decoded again by the exact one-symbol loop below, which also
+// finishes every span (end-of-stream rules of huffman.c:196-211, 240-255).
+// ---------------------------------------------------------------------------------------------
+struct Lut2 {
+    uint32_t addr;     // shared-window address of entry 0 (32-byte aligned)
+    uint32_t root_ns;  // y of "next step: root table" = addr | (32 - root_bits)
+    uint32_t trap_tb;  // table address of the trap table
+};
+
+// copies the table into shared memory, turning table offsets into shared-window addresses
+__device__ __forceinline__ Lut2 lut2_load(uint2 *s_lut2, const uint2 *g_lut2, uint32_t count, uint32_t root_bits, uint32_t trap_base) {
+    Lut2 t;
+    t.addr = (uint32_t)__cvta_generic_to_shared(s_lut2);
+    t.root_ns = t.addr | (32u - root_bits);
+    t.trap_tb = t.addr + 8u * trap_base;
+    for (uint32_t i = threadIdx.x; i < count; i += blockDim.x) {
+        uint2 e = g_lut2[i];
+        e.y += t.addr;
+        s_lut2[i] = e;
+    }
+    return t;
+}
+
+struct Lut2Hit {
+    uint32_t x;      // entry (0: no code matches the window)
+    uint32_t total;  // bits of the whole entry (one or two codes)
+};
+// exact lookup of one window (one symbol at a time callers use len1 / symbol 1 of x)
+__device__ __forceinline__ Lut2Hit lut2_lookup(const Lut2 &t, uint32_t window) {
+    uint32_t ns = t.root_ns, used = 0;
+    Lut2Hit h;
+    while (true) {
+        const uint32_t tb = ns & 0x00ffffe0u;
+        const uint32_t idx = (window << used) >> (ns & 31u);
+        uint32_t x, y;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(x), "=r"(y) : "r"(tb + 8u * idx));
+        const uint32_t adv = y >> 24;
+        if (x >> 30) {
+            h.x = x;
+            h.total = used + adv;
+            return h;
+        }
+        if (adv == 0) {
+            h.x = 0;
+            h.total = 0;
+            return h;
+        }
+        used += adv;
+        ns = y;
+    }
+}
+__device__ __forceinline__ uint32_t lut2_len1(uint32_t x) { return (x >> 16) & 63u; }
+
+template <bool kEmit, bool kPadded, bool kSkipHoles>
+__device__ __forceinline__ SpanS decode_span_lean(
+    const uint32_t *s_in, const Lut2 &t, uint32_t root_bits, uint32_t pos, uint32_t stop, uint32_t end, uint32_t out_addr) {
+    constexpr uint32_t kParked = 0x80000000u;
+    const uint32_t out0 = out_addr, pos0 = pos;
+    SpanS r;
+    r.term = kTermStop;
+    if (pos < stop) {
+        const uint32_t fast_end = (end >= 32u) ? min(stop, end - 31u) : 0u;
+        const uint32_t pair_end = fast_end > root_bits ? fast_end - root_bits : 0u;
+        const uint32_t in_addr = (uint32_t)__cvta_generic_to_shared(s_in);
+        StreamCursor c;
+        c.init<kPadded>(in_addr, pos);
+        uint32_t ns = t.root_ns, tb = t.addr;
+        const uint32_t root_tb = t.addr;
+        uint32_t acc = 0;  // (kEmit) symbols not stored yet: the low out_addr & 3 bytes
+        while (pos < pair_end || tb != root_tb) {
+#pragma unroll
+            for (int step = 0; step < kUnifiedSteps; ++step) {
+                if (kEmit) {
+                    // symbols are collected in `acc` (little-endian, out & 3 bytes pending) and leave as whole
+                    // 32-bit words: a quarter of the stores of the byte-by-byte version, and those were 40 % of the
+                    // kernel's shared-memory wavefronts (the decode phase is bound by them, not by issue slots)
+                    asm volatile(
+                        "{\n\t"
+                        ".reg .pred p, c, w;\n\t"
+                        ".reg .b32 win, idx, adr, x, u, t, sh, lo, sp, no, wadr;\n\t"
+                        "setp.lt.u32 p, %0, %10;\n\t"
+                        "setp.ne.or.u32 p, %8, %11, p;\n\t"
+                        "shf.l.wrap.b32 win, %2, %1, %0;\n\t"
+                        "shf.r.wrap.b32 idx, win, 0, %7;\n\t"
+                        "mad.lo.u32 adr, idx, 8, %8;\n\t"
+                        "mov.b32 x, 0;\n\t"
+                        "@p ld.shared.v2.u32 {x, %7}, [adr];\n\t"
+                        "and.b32 %8, %7, 0x00ffffe0;\n\t"
+                        "shr.u32 u, %7, 24;\n\t"
+                        "@p add.u32 %0, %0, u;\n\t"
+                        "and.b32 t, x, 0xffff;\n\t"
+                        "shl.b32 sh, %6, 3;\n\t"
+                        "shf.l.wrap.b32 lo, 0, t, sh;\n\t"
+                        "shf.l.wrap.b32 sp, t, 0, sh;\n\t"
+                        "or.b32 lo, lo, %9;\n\t"
+                        "shr.u32 u, x, 30;\n\t"
+                        "add.u32 no, %6, u;\n\t"
+                        "xor.b32 u, no, %6;\n\t"
+                        "and.b32 u, u, 4;\n\t"
+                        "setp.ne.u32 w, u, 0;\n\t"
+                        "and.b32 wadr, %6, 0xfffffffc;\n\t"
+                        "@w st.shared.u32 [wadr], lo;\n\t"
+                        "selp.b32 %9, sp, lo, w;\n\t"
+                        "mov.b32 %6, no;\n\t"
+                        "setp.ge.s32 c, %0, %5;\n\t"
+                        "@c mov.b32 %1, %2;\n\t"
+                        "@c mov.b32 %2, %3;\n\t"
+                        "@c ld.shared.u32 %3, [%4];\n\t"
+                        "@c add.u32 %4, %4, 4;\n\t"
+                        "@c add.s32 %5, %5, 32;\n\t"
+                        "}"
+                        : "+r"(pos), "+r"(c.w0), "+r"(c.w1), "+r"(c.w2), "+r"(c.wa), "+r"(c.limit), "+r"(out_addr), "+r"(ns), "+r"(tb), "+r"(acc)
+                        : "r"(pair_end), "r"(root_tb)
+                        : "memory");
+                } else {
+                    asm volatile(
+                        "{\n\t"
+                        ".reg .pred p, c;\n\t"
+                        ".reg .b32 win, idx, adr, x, u;\n\t"
+                        "setp.lt.u32 p, %0, %8;\n\t"
+                        "setp.ne.or.u32 p, %7, %9, p;\n\t"
+                        "shf.l.wrap.b32 win, %2, %1, %0;\n\t"
+                        "shf.r.wrap.b32 idx, win, 0, %6;\n\t"
+                        "mad.lo.u32 adr, idx, 8, %7;\n\t"
+                        "@p ld.shared.v2.u32 {x, %6}, [adr];\n\t"
+                        "and.b32 %7, %6, 0x00ffffe0;\n\t"
+                        "shr.u32 u, %6, 24;\n\t"
+                        "@p add.u32 %0, %0, u;\n\t"
+                        "setp.ge.s32 c, %0, %5;\n\t"
+                        "@c mov.b32 %1, %2;\n\t"
+                        "@c mov.b32 %2, %3;\n\t"
+                        "@c ld.shared.u32 %3, [%4];\n\t"
+                        "@c add.u32 %4, %4, 4;\n\t"
+                        "@c add.s32 %5, %5, 32;\n\t"
+                        "}"
+                        : "+r"(pos), "+r"(c.w0), "+r"(c.w1), "+r"(c.w2), "+r"(c.wa), "+r"(c.limit), "+r"(ns), "+r"(tb)
+                        : "r"(pair_end), "r"(root_tb)
+                        : "memory");
+                }
+            }
+            if (tb == t.trap_tb) {  // no code matches: leave the loop, the exact loop below redoes the span
+                pos |= kParked;
+                tb = root_tb;
+            }
+        }
+        if (pos & kParked) {
+            pos = pos0;
+            out_addr = out0;
+            c.init<kPadded>(in_addr, pos);
+        } else if (kEmit && (out_addr & 3u)) {
+            // the symbols still in `acc` (the bytes above them are spare: rows have slack)
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(out_addr & ~3u), "r"(acc) : "memory");
+        }
+        // the rest of the span (or all of it, after a trap): one lookup at a time with the end-of-stream rules (the
+        // window is the stream zero-extended, huffman.c:196-211; a code that does not fit ends the stream,
+        // :240-255). A two-symbol entry still counts when its second code starts before `stop` and ends inside
+        // the stream.
+        while (r.term == kTermStop && pos < stop) {
+            const uint32_t left = end - pos;  // >= 1
+            uint32_t window = c.window(pos);
+            if (left < 32u) window &= 0xffffffffu << (32u - left);
+            const Lut2Hit h = lut2_lookup(t, window);
+            if (h.x == 0) {
+                if (kSkipHoles && left > 1u) {
+                    ++pos;
+                    c.follow(pos);
+                    continue;
+                }
+                r.term = left < 32u ? kTermEnd : kTermUnknown;  // fewer than 32 bits left: padding
+                break;
+            }
+            const uint32_t len1 = lut2_len1(h.x);
+            if (len1 > left) {
+                r.term = kTermEnd;  // a code cut short by the end of the stream
+                break;
+            }
+            const bool two = (h.x >> 30) == 2u && pos + len1 < stop && h.total <= left;
+            if (kEmit) {
+                sts_u8(out_addr, h.x);
+                if (two) sts_u8(out_addr + 1, h.x >> 8);
+                out_addr += two ? 2u : 1u;
+            }
+            pos += two ? h.total : len1;
+            c.follow(pos);
+        }
+    }
+    if (r.term == kTermStop && pos >= end) r.term = kTermEnd;
+    r.pos = pos;
+    r.nsym = out_addr - out0;
+    return r;
+}
+
+// decode_span (bit reader over global memory) with the shared-memory LUT2: the route of tiles that do not fit the stage
+template <bool kWrite>
+__device__ __forceinline__ DecodeSpan decode_span_lut2(
+    const Lut2 &t, const uint8_t *base, uint64_t start, uint64_t stop, uint64_t end_byte, ByteWriter *writer) {
+    const uint64_t end_bit = end_byte * 8;
+    DecodeSpan r;
+    r.pos = start;
+    r.nsym = 0;
+    r.term = kTermStop;
+    if (start >= stop) {
+        if (start >= end_bit) r.term = kTermEnd;
+        return r;
+    }
+    BitReader br;
+    br.init(base, start, end_byte);
+    uint64_t pos = start, nsym = 0;
+    while (true) {
+        br.refill();
+        const Lut2Hit h = lut2_lookup(t, br.window());
+        const uint64_t bits_left = end_bit - pos;
+        if (h.x == 0) {
+            r.term = bits_left < 32 ? kTermEnd : kTermUnknown;
+            break;
+        }
+        const uint32_t used = lut2_len1(h.x);
+        if (used > bits_left) { r.term = kTermEnd; break; }
+        br.consume(used);
+        pos += used;
+        ++nsym;
+        if (kWrite) writer->put(h.x & 0xffu);
+        if (pos >= stop) {
+            if (pos >= end_bit) r.term = kTermEnd;
+            break;
+        }
+    }
+    r.pos = pos;
+    r.nsym = nsym;
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Batch of independent strings
 // ---------------------------------------------------------------------------------------------
+#ifdef HB_PHASE_TIMING  // (development builds: cycles per phase of decode_batch_kernel, thread 0 of every block)
+#define HB_PHASE_MARK(i)                                                   \
+    do {                                                                   \
+        if (tid == 0) {                                                    \
+            const long long now_ = clock64();                              \
+            atomicAdd(&hb_phase_cycles[i], (unsigned long long)(now_ - t_phase_)); \
+            t_phase_ = now_;                                               \
+        }                                                                  \
+    } while (0)
+#else
+#define HB_PHASE_MARK(i) do { } while (0)
+#endif
+
 constexpr int kDecThreads = 256;
 constexpr int kDecWarps = kDecThreads / 32;
+constexpr int kDecBlock = kDecThreads + 32;  // a team: 8 worker warps + 1 scout warp
+constexpr int kDecTeams = 2;                 // teams per block (they share the decode table)
+constexpr uint32_t kDecDone = 0xffffffffu;
 constexpr int kDecItemsPerTile = 288;        // strings per tile (9 groups of 32)
+// Named barriers (as in encode_tiled.cuh). Workers among themselves: 1. Hand-off of a tile to the scout: 2 + parity
+// (workers arrive without waiting, the scout waits). Result of a look-back: 4 + parity (the scout arrives, the
+// workers wait).
+__device__ __forceinline__ void dec_worker_sync(uint32_t team) { asm volatile("bar.sync %0, %1;" ::"r"(5 * team + 1), "n"(kDecThreads) : "memory"); }
+__device__ __forceinline__ void dec_bar_arrive(uint32_t id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(kDecBlock) : "memory"); }
+__device__ __forceinline__ void dec_bar_sync(uint32_t id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kDecBlock) : "memory"); }
 constexpr uint32_t kDecMaxRow = 4096;        // a staged string decodes to at most this many bytes
 constexpr uint32_t kDecRowSlack = 8;         // spare bytes per row (alignment, the emitter's look-ahead byte)
 
 struct DecBatchArgs {
     BatchView b;
-    const uint32_t *lut;
-    uint32_t lut_count;
+    const uint32_t *lut;   // 32-bit table in global memory (the rare tiles that do not fit the stage)
+    const uint2 *lut2;     // 64-bit entries of the lean step, copied to shared memory
+    uint32_t lut2_count;   // entries (a multiple of 4)
+    uint32_t lut2_trap;    // first entry of the trap table
     uint32_t root_bits;
     uint32_t min_len;      // shortest code: a string of L bytes decodes to at most 8 L / min_len symbols
     uint32_t stage_words;  // capacity of the input stage
@@ -588,19 +858,35 @@ struct DecBatchArgs {
     uint32_t num_tiles;
     uint32_t items_per_tile;  // <= kDecItemsPerTile, a multiple of 32: fewer when the strings are long, so that a
                               // tile of average strings still fits the stage
-    uint8_t *scratch;       // deferred output: one slot of scratch_slot bytes per block (16-byte aligned)
-    uint32_t scratch_slot;
 };
 
-// Whole block: the tile whose dense image sits in `slot` goes to its final place, `tile_base` being known now.
-__device__ __forceinline__ void dec_flush_tile(
-    const BatchView &b, const uint8_t *slot, uint64_t tile_base, uint32_t total, uint64_t item0, uint32_t nitems,
-    const uint32_t *s_off_tile) {
-    for (uint32_t it = threadIdx.x; it < nitems; it += blockDim.x) b.out_offsets[item0 + it] = tile_base + s_off_tile[it];
-    if (threadIdx.x == 0 && item0 + nitems == b.n) b.out_offsets[b.n] = tile_base + total;
-    const uint64_t room = tile_base < b.out_capacity ? b.out_capacity - tile_base : 0;
-    const uint32_t ncopy = (uint32_t)min((uint64_t)total, room);
-    block_copy_realign(slot, b.out + tile_base, ncopy, threadIdx.x, blockDim.x);
+// Whole team: copies n bytes of a dense image in shared memory (`src` 16-byte aligned, with >= 32 readable bytes
+// after n) to `dst` (any alignment) with 128-bit stores.
+__device__ __forceinline__ void smem_copy_out(const uint8_t *src, uint8_t *dst, uint32_t n, uint32_t tid, uint32_t nthreads) {
+    const uint32_t head = min(n, (16u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15)) & 15u);
+    const uint32_t nvec = (n - head) >> 4;
+    const uint4 *sv = reinterpret_cast<const uint4 *>(src);
+    uint4 *dv = reinterpret_cast<uint4 *>(dst + head);
+    const uint32_t tw = head >> 2, r8 = (head & 3u) * 8u;  // the body starts `head` bytes into the image
+    for (uint32_t v = tid; v < nvec; v += nthreads) {
+        const uint4 a = sv[v], b = sv[v + 1];
+        uint32_t w0, w1, w2, w3, w4;
+        switch (tw) {  // (uniform)
+            case 0: w0 = a.x; w1 = a.y; w2 = a.z; w3 = a.w; w4 = b.x; break;
+            case 1: w0 = a.y; w1 = a.z; w2 = a.w; w3 = b.x; w4 = b.y; break;
+            case 2: w0 = a.z; w1 = a.w; w2 = b.x; w3 = b.y; w4 = b.z; break;
+            default: w0 = a.w; w1 = b.x; w2 = b.y; w3 = b.z; w4 = b.w; break;
+        }
+        uint4 o;
+        o.x = __funnelshift_r(w0, w1, r8);
+        o.y = __funnelshift_r(w1, w2, r8);
+        o.z = __funnelshift_r(w2, w3, r8);
+        o.w = __funnelshift_r(w3, w4, r8);
+        dv[v] = o;
+    }
+    if (tid < head) dst[tid] = src[tid];
+    const uint32_t tail0 = head + 16u * nvec;
+    if (tid >= 32 && tid - 32 < n - tail0) dst[tail0 + tid - 32] = src[tail0 + tid - 32];
 }
 
 // Thread-serial copy of n bytes inside shared memory; src is 4-byte aligned, dst is not.
@@ -655,49 +941,103 @@ __device__ __forceinline__ void smem_copy_row(const uint8_t *src, uint8_t *dst, 
 // kFramed: the items are HPACK string literals (hpack_literals.cuh): the string table parses each literal's H bit and
 // length (the payload is what gets staged / decoded), raw literals are copied instead of decoded, and the padding rule
 // of RFC 7541 5.2 is applied to what the decoder leaves over; items with a non-zero status decode to nothing.
+// Shared state of one TEAM (8 worker warps + 1 scout warp working on one tile). A block holds kDecTeams teams
+// that share ONE copy of the decode table: the table is 38 KB, and what bounds this kernel is the number of
+// strings in flight per SM (every phase of a tile is a chain of latencies), so the shared memory a second copy
+// would take is worth more as stage and rows.
 template <bool kFramed>
-__global__ void __launch_bounds__(kDecThreads, 2) decode_batch_kernel(DecBatchArgs a) {
-    extern __shared__ __align__(16) uint32_t s_lut[];  // [LUT][stage][rows]
-    const uint32_t lut_pad = (a.lut_count + 3u) & ~3u;
-    uint32_t *s_in = s_lut + lut_pad;
-    uint8_t *const s_dense = reinterpret_cast<uint8_t *>(s_in);  // the dense image starts where the stage does
-    const uint32_t stage_bytes = (a.stage_words + 2) * 4;         // (+2 zero words for the window look-ahead)
-    uint8_t *const s_rows = s_dense + ((stage_bytes + 15u) & ~15u);
-    __shared__ uint32_t s_start[kDecItemsPerTile];  // first bit of the string in the stage
-    __shared__ uint32_t s_bytes[kDecItemsPerTile];  // encoded length
-    __shared__ uint32_t s_cnt[kDecItemsPerTile];    // symbols per string
-    __shared__ uint32_t s_off[2][kDecItemsPerTile]; // exclusive offsets within the tile (this tile's and the pending one's)
-    __shared__ uint32_t s_row[kDecItemsPerTile];    // start of the string's row in the row area
-    __shared__ uint16_t s_perm[kDecItemsPerTile];   // strings in order of decreasing length
-    __shared__ uint8_t s_flag[kFramed ? kDecItemsPerTile : 1];  // framed: bit 0 raw payload, bit 1 malformed literal
+struct DecTeamShared {
+    uint32_t start[kDecItemsPerTile];   // first bit of the string in the stage
+    uint32_t bytes[kDecItemsPerTile];   // encoded length
+    uint32_t cnt[kDecItemsPerTile];     // symbols per string
+    uint32_t off[2][kDecItemsPerTile];  // exclusive offsets within the tile (this tile's and the pending one's)
+    uint32_t row[kDecItemsPerTile];     // start of the string's row in the row area
+    uint16_t perm[kDecItemsPerTile];    // strings in order of decreasing length
+    uint8_t flag[kFramed ? kDecItemsPerTile : 4];  // framed: bit 0 raw payload, bit 1 malformed literal
+    uint32_t hist[256];
+    uint64_t warp_sum[kDecWarps];
+    uint32_t tile, next, fits, total;
+    uint32_t hand_tile[2];                 // workers -> scout, by hand-off parity
+    uint64_t hand_prefix[2];               // scout -> workers
+};
+
+template <bool kFramed>
+__global__ void __launch_bounds__(kDecTeams * kDecBlock, 1) decode_batch_kernel(DecBatchArgs a) {
+    extern __shared__ __align__(128) uint32_t s_lut[];  // [LUT2][team 0: stage, rows][team 1: stage, rows]
+    __shared__ DecTeamShared<kFramed> s_teams[kDecTeams];
     static_assert(kDecItemsPerTile <= 2 * kDecThreads, "the block scan handles two strings per thread");
-    __shared__ uint32_t s_hist[256];
-    __shared__ uint64_t s_warp_sum[kDecWarps];
-    __shared__ uint64_t s_prefix, s_prefix_now;
-    __shared__ uint32_t s_tile, s_next, s_fits, s_total;
+    const uint32_t team = threadIdx.x / kDecBlock, tid = threadIdx.x - team * kDecBlock;
+    DecTeamShared<kFramed> &sh = s_teams[team];
+    uint32_t (&s_start)[kDecItemsPerTile] = sh.start;
+    uint32_t (&s_bytes)[kDecItemsPerTile] = sh.bytes;
+    uint32_t (&s_cnt)[kDecItemsPerTile] = sh.cnt;
+    uint32_t (&s_off)[2][kDecItemsPerTile] = sh.off;
+    uint32_t (&s_row)[kDecItemsPerTile] = sh.row;
+    uint16_t (&s_perm)[kDecItemsPerTile] = sh.perm;
+    auto &s_flag = sh.flag;
+    uint32_t (&s_hist)[256] = sh.hist;
+    uint64_t (&s_warp_sum)[kDecWarps] = sh.warp_sum;
+    uint32_t &s_tile = sh.tile, &s_next = sh.next, &s_fits = sh.fits, &s_total = sh.total;
+    uint32_t (&s_hand_tile)[2] = sh.hand_tile;
+    uint64_t (&s_hand_prefix)[2] = sh.hand_prefix;
+    const uint32_t lut_pad = 2u * a.lut2_count;          // words
+    const uint32_t stage_bytes = (a.stage_words + 2) * 4;         // (+2 zero words for the window look-ahead)
+    const uint32_t team_bytes = ((stage_bytes + 15u) & ~15u) + a.rows_bytes + 64u;
+    uint32_t *s_in = s_lut + lut_pad + team * (team_bytes / 4);
+    uint8_t *const s_dense = reinterpret_cast<uint8_t *>(s_in);  // the dense image starts where the stage does
+    uint8_t *const s_rows = s_dense + ((stage_bytes + 15u) & ~15u);
 
-    for (uint32_t i = threadIdx.x; i < a.lut_count; i += kDecThreads) s_lut[i] = a.lut[i];
-    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    const Lut2 lut2 = lut2_load(reinterpret_cast<uint2 *>(s_lut), a.lut2, a.lut2_count, a.root_bits, a.lut2_trap);
+    const uint32_t lane = lane_id(), warp = tid >> 5;
     const BatchView &b = a.b;
+    __syncthreads();  // the LUT is in place
+    // ================================ scout =====================================================================
+    // The ninth warp resolves where the tile's output starts — the sum of the symbol counts of ALL tiles before it
+    // (single-pass decoupled look-back) — WHILE the workers stage, decode and compact the tile: the sum does not
+    // need the tile's own count, only its predecessors', and those finish at about the same time (tiles are
+    // handed out in order). By the time the dense image is ready the position is normally known, so the image goes
+    // straight from shared memory to its final place: no parking in a scratch slot, no second copy (round 1 parked
+    // every tile for one tile's time because warp 0 only started the look-back after the decode: 14-25 % of the
+    // kernel was the wait for that chain of L2 round trips).
+    if (warp == kDecWarps) {
+        for (uint32_t h = 0;; ++h) {
+            dec_bar_sync(5 * team + 2 + (h & 1));  // the workers took a tile
+            const uint32_t t = s_hand_tile[h & 1];
+            if (t == kDecDone) return;
+#ifdef HB_ABL_DEC_NO_LOOKBACK  // (timing-only ablation: wrong output positions)
+            const uint64_t prefix = 0;
+#else
+            const uint64_t prefix = lookback_exclusive(a.tile_state, t);
+#endif
+            if (lane == 0) s_hand_prefix[h & 1] = prefix;
+            dec_bar_arrive(5 * team + 4 + (h & 1));  // result ready
+        }
+    }
+    // ================================ workers ===================================================================
+    uint32_t hand = 0;  // tiles handed to the scout so far
     const uint32_t rows_addr = (uint32_t)__cvta_generic_to_shared(s_rows);
-    uint8_t *const slot = a.scratch + (size_t)blockIdx.x * a.scratch_slot;  // this block's deferred-output slot
-    // the tile whose image sits in the slot (block-uniform)
-    bool pend = false;
-    uint32_t pend_tile = 0, pend_total = 0, pend_nitems = 0;
-    uint64_t pend_item0 = 0;
 
+#ifdef HB_PHASE_TIMING
+    long long t_phase_ = clock64();
+#endif
     uint32_t iter = 0;
     for (;; ++iter) {
-        __syncthreads();  // previous tile fully done (and the LUT is in place on the first trip)
-        if (threadIdx.x == 0) {
+        dec_worker_sync(team);  // previous tile fully done (and the LUT is in place on the first trip)
+        if (tid == 0) {
             s_tile = atomicAdd(a.ticket, 1u);
             s_next = kDecWarps;
             s_fits = 1;
         }
-        for (uint32_t i = threadIdx.x; i < 256; i += kDecThreads) s_hist[i] = 0;
-        __syncthreads();
+        for (uint32_t i = tid; i < 256; i += kDecThreads) s_hist[i] = 0;
+        dec_worker_sync(team);
         const uint32_t tile = s_tile;
         if (tile >= a.num_tiles) break;
+        if (tid == 0) s_hand_tile[hand & 1] = tile;
+        dec_bar_arrive(5 * team + 2 + (hand & 1));  // the scout starts on the tile's position
+        ++hand;
+#ifdef HB_PHASE_TIMING
+        if (tid == 0 && tile < 8192) hb_tile_times[0][tile] = hb_now_ns();
+#endif
         const uint64_t item0 = (uint64_t)tile * a.items_per_tile;
         const uint32_t nitems = (uint32_t)min((uint64_t)a.items_per_tile, b.n - item0);
         const uint32_t ngroups = (nitems + 31) / 32;
@@ -710,7 +1050,7 @@ __global__ void __launch_bounds__(kDecThreads, 2) decode_batch_kernel(DecBatchAr
         // row i starts at 4 * ceil(2 * offset / min_len) + slack * i: never before the end of row i - 1
         const uint64_t rows_need = 4 * ((2 * (byte1 - byte0) + a.min_len - 1) / a.min_len) + (uint64_t)kDecRowSlack * (nitems + 1);
         bool fits = nwords64 <= a.stage_words && rows_need <= a.rows_bytes;
-        for (uint32_t it = threadIdx.x; it < nitems; it += kDecThreads) {
+        for (uint32_t it = tid; it < nitems; it += kDecThreads) {
             const uint64_t in0 = b.in_offsets[item0 + it];
             uint64_t len = b.in_offsets[item0 + it + 1] - in0;
             uint64_t skip = 0;  // bytes of the item before its payload
@@ -729,14 +1069,14 @@ __global__ void __launch_bounds__(kDecThreads, 2) decode_batch_kernel(DecBatchAr
             if (8 * len / a.min_len + kDecRowSlack > kDecMaxRow) s_fits = 0;
             atomicAdd(&s_hist[255 - (uint32_t)min(len, (uint64_t)255)], 1u);
         }
-        __syncthreads();
+        dec_worker_sync(team);
         const bool staged = fits && s_fits != 0;
         if (staged) {
             // ---- stage the tile's encoded bytes as big-endian words -------------------------------------------
             const uint32_t nwords = (uint32_t)nwords64;
             const uint32_t nquads = nwords >> 2;  // whole 128-bit loads; the ragged end goes word by word
             const uint4 *g4 = reinterpret_cast<const uint4 *>(addr0 - lead);
-            for (uint32_t j = threadIdx.x; j < nquads; j += kDecThreads) {
+            for (uint32_t j = tid; j < nquads; j += kDecThreads) {
                 const uint4 v = __ldg(g4 + j);
                 uint4 o;
                 o.x = __byte_perm(v.x, 0, 0x0123);
@@ -746,9 +1086,9 @@ __global__ void __launch_bounds__(kDecThreads, 2) decode_batch_kernel(DecBatchAr
                 reinterpret_cast<uint4 *>(s_in)[j] = o;
             }
             const uint32_t *gw = reinterpret_cast<const uint32_t *>(addr0 - lead);
-            for (uint32_t j = 4 * nquads + threadIdx.x; j < nwords; j += kDecThreads)
+            for (uint32_t j = 4 * nquads + tid; j < nwords; j += kDecThreads)
                 s_in[j] = __byte_perm(__ldg(gw + j), 0, 0x0123);
-            if (threadIdx.x < 2) s_in[nwords + threadIdx.x] = 0;
+            if (tid < 2) s_in[nwords + tid] = 0;
         }
         if (warp == 0) {
             // exclusive scan of the 256 bins, 8 per lane
@@ -765,13 +1105,14 @@ __global__ void __launch_bounds__(kDecThreads, 2) decode_batch_kernel(DecBatchAr
                 run += v[i];
             }
         }
-        __syncthreads();
-        for (uint32_t it = threadIdx.x; it < nitems; it += kDecThreads) {
+        dec_worker_sync(team);
+        for (uint32_t it = tid; it < nitems; it += kDecThreads) {
             const uint32_t rank = atomicAdd(&s_hist[255 - min(s_bytes[it], 255u)], 1u);
             s_perm[rank] = (uint16_t)it;
         }
-        __syncthreads();
+        dec_worker_sync(team);
 
+        HB_PHASE_MARK(0);  // ticket, string table, staging, sort
         // ---- decode (staged: once, into the rows; otherwise: count) ------------------------------------------
         for (uint32_t g = warp; g < ngroups;) {
             const uint32_t slot = g * 32 + lane;
@@ -796,7 +1137,7 @@ __global__ void __launch_bounds__(kDecThreads, 2) decode_batch_kernel(DecBatchAr
                     }
                 } else if (staged) {
                     const uint32_t ib = s_start[it], ie = ib + nbytes * 8;
-                    const SpanS r = decode_span_smem<true, false, false>(s_in, s_lut, a.root_bits, ib, ie, ie, rows_addr + s_row[it]);
+                    const SpanS r = decode_span_lean<true, false, false>(s_in, lut2, a.root_bits, ib, ie, ie, rows_addr + s_row[it]);
                     cbits = r.pos - ib;
                     nsym = r.nsym;
                     term = r.term;
@@ -807,7 +1148,7 @@ __global__ void __launch_bounds__(kDecThreads, 2) decode_batch_kernel(DecBatchAr
                     }
                 } else {
                     const uint64_t len = kFramed ? (uint64_t)nbytes : b.in_offsets[item + 1] - b.in_offsets[item];
-                    const DecodeSpan r = decode_span<false, false>(s_lut, a.root_bits, payload, 0, len * 8, len, nullptr);
+                    const DecodeSpan r = decode_span_lut2<false>(lut2, payload, 0, len * 8, len, nullptr);
                     cbits = r.pos;
                     nsym = (uint32_t)r.nsym;
                     term = r.term;
@@ -835,16 +1176,17 @@ __global__ void __launch_bounds__(kDecThreads, 2) decode_batch_kernel(DecBatchAr
             if (lane == 0) next = atomicAdd(&s_next, 1u);
             g = __shfl_sync(0xffffffffu, next, 0);
         }
-        __syncthreads();
+        dec_worker_sync(team);
 
+        HB_PHASE_MARK(1);  // decode (to the barrier behind it)
         // ---- offsets: block scan (2 strings per thread); the tile's count goes out at once ------------------------
         const uint32_t par = iter & 1u;
-        const uint32_t c0 = 2 * threadIdx.x < nitems ? s_cnt[2 * threadIdx.x] : 0u;
-        const uint32_t c1 = 2 * threadIdx.x + 1 < nitems ? s_cnt[2 * threadIdx.x + 1] : 0u;
+        const uint32_t c0 = 2 * tid < nitems ? s_cnt[2 * tid] : 0u;
+        const uint32_t c1 = 2 * tid + 1 < nitems ? s_cnt[2 * tid + 1] : 0u;
         const uint64_t mine = (uint64_t)c0 + c1;
         const uint64_t incl = warp_inclusive_scan64(mine);
         if (lane == 31) s_warp_sum[warp] = incl;
-        __syncthreads();
+        dec_worker_sync(team);
         if (warp == 0) {
             uint64_t w = lane < kDecWarps ? s_warp_sum[lane] : 0;
             const uint64_t wi = warp_inclusive_scan64(w);
@@ -853,39 +1195,28 @@ __global__ void __launch_bounds__(kDecThreads, 2) decode_batch_kernel(DecBatchAr
             if (lane == 0) {
                 lookback_publish_aggregate(a.tile_state, tile, total);
                 s_total = (uint32_t)total;
+#ifdef HB_PHASE_TIMING
+                if (tile < 8192) hb_tile_times[1][tile] = hb_now_ns();
+#endif
             }
         }
-        __syncthreads();
+        dec_worker_sync(team);
         {
             const uint64_t e0 = s_warp_sum[warp] + (incl - mine);  // exclusive, within the tile
-            if (2 * threadIdx.x < nitems) {
-                s_off[par][2 * threadIdx.x] = (uint32_t)e0;
-                if (b.out_lens) b.out_lens[item0 + 2 * threadIdx.x] = c0;
+            if (2 * tid < nitems) {
+                s_off[par][2 * tid] = (uint32_t)e0;
+                if (b.out_lens) b.out_lens[item0 + 2 * tid] = c0;
             }
-            if (2 * threadIdx.x + 1 < nitems) {
-                s_off[par][2 * threadIdx.x + 1] = (uint32_t)(e0 + c0);
-                if (b.out_lens) b.out_lens[item0 + 2 * threadIdx.x + 1] = c1;
+            if (2 * tid + 1 < nitems) {
+                s_off[par][2 * tid + 1] = (uint32_t)(e0 + c0);
+                if (b.out_lens) b.out_lens[item0 + 2 * tid + 1] = c1;
             }
-            if (threadIdx.x == 0) s_next = kDecWarps;
+            if (tid == 0) s_next = kDecWarps;
         }
-        __syncthreads();
+        dec_worker_sync(team);
         const uint32_t total = s_total;
 
-        // ---- DEFERRED OUTPUT: where a tile's output goes depends on every tile before it. Waiting for that
-        // right here costs 14 % of the kernel (measured: blocks stand still until the slowest predecessor in
-        // flight has counted). So the tile's dense image goes to this block's scratch slot (L2-resident) and
-        // the block moves on; the prefix of the PREVIOUS tile, resolved by warp 0 while the other warps build
-        // this tile's image, is surely there by now, and that tile's bytes and offsets go to their final place.
-        if (warp == 0) {
-            if (pend) {
-                const uint64_t prefix = lookback_resolve(a.tile_state, pend_tile, pend_total);
-                if (lane == 0) s_prefix = prefix;
-            }
-            if (!staged) {  // (two-pass route: needs its own prefix right away)
-                const uint64_t prefix = lookback_resolve(a.tile_state, tile, total);
-                if (lane == 0) s_prefix_now = prefix;
-            }
-        }
+        HB_PHASE_MARK(2);  // scan, publish
         if (staged) {
             // rows -> dense image at the front of the stage area. Rows that start before `front` lie where the
             // image may grow: they go first (their destination ends inside the stage area); the host sizes the
@@ -893,36 +1224,29 @@ __global__ void __launch_bounds__(kDecThreads, 2) decode_batch_kernel(DecBatchAr
             const uint32_t front = stage_bytes > kDecMaxRow + 32 ? ((stage_bytes - kDecMaxRow - 32) & ~3u) : 0u;
 #pragma unroll 1
             for (int phase = 0; phase < 2; ++phase) {
-                for (uint32_t it = threadIdx.x; it < nitems; it += kDecThreads) {
+                for (uint32_t it = tid; it < nitems; it += kDecThreads) {
                     const uint32_t row = s_row[it];
 #ifndef HB_ABL_NO_COPY
                     if ((row < front) == (phase == 0)) smem_copy_row(s_rows + row, s_dense + s_off[par][it], s_cnt[it]);
 #endif
                 }
-                __syncthreads();
+                dec_worker_sync(team);
             }
-        } else {
-            __syncthreads();
         }
-        if (pend) {
-            dec_flush_tile(b, slot, s_prefix, pend_total, pend_item0, pend_nitems, s_off[par ^ 1u]);
-            __syncthreads();  // the slot is free again
-        }
-        pend = staged;
+        HB_PHASE_MARK(3);  // rows -> image
+        // ---- where the tile goes: the scout has been summing its predecessors since the tile was taken --------------
+        dec_bar_sync(5 * team + 4 + ((hand - 1) & 1));
+        const uint64_t tile_base = s_hand_prefix[(hand - 1) & 1];
+        if (tid == 0 && tile > 0)
+            st_relaxed_u64(&a.tile_state[tile], (kLbPrefix << kLbFlagShift) | ((tile_base + total) & kLbValueMask));
+        for (uint32_t it = tid; it < nitems; it += kDecThreads) b.out_offsets[item0 + it] = tile_base + s_off[par][it];
+        if (tid == 0 && item0 + nitems == b.n) b.out_offsets[b.n] = tile_base + total;
+        HB_PHASE_MARK(4);  // wait for the position
         if (staged) {
-            const uint32_t nvec = (total + 15u) >> 4;
-            const uint4 *sv = reinterpret_cast<const uint4 *>(s_dense);
-            uint4 *gv = reinterpret_cast<uint4 *>(slot);
-            for (uint32_t v = threadIdx.x; v < nvec; v += kDecThreads) gv[v] = sv[v];
-            pend_tile = tile;
-            pend_total = total;
-            pend_item0 = item0;
-            pend_nitems = nitems;
+            const uint64_t room = tile_base < b.out_capacity ? b.out_capacity - tile_base : 0;
+            smem_copy_out(s_dense, b.out + tile_base, (uint32_t)min((uint64_t)total, room), tid, kDecThreads);
         } else {
             // ---- write: decode again from global memory, now storing --------------------------------------------------
-            const uint64_t tile_base = s_prefix_now;
-            for (uint32_t it = threadIdx.x; it < nitems; it += kDecThreads) b.out_offsets[item0 + it] = tile_base + s_off[par][it];
-            if (threadIdx.x == 0 && item0 + nitems == b.n) b.out_offsets[b.n] = tile_base + total;
             for (uint32_t g = warp; g < ngroups;) {
                 const uint32_t gslot = g * 32 + lane;
                 if (gslot < nitems) {
@@ -938,7 +1262,7 @@ __global__ void __launch_bounds__(kDecThreads, 2) decode_batch_kernel(DecBatchAr
                     } else {
                         ByteWriter wr;
                         wr.init(b.out + off, room);
-                        decode_span<true, false>(s_lut, a.root_bits, b.in + in0, 0, len * 8, len, &wr);
+                        decode_span_lut2<true>(lut2, b.in + in0, 0, len * 8, len, &wr);
                         wr.finish();
                     }
                 }
@@ -947,16 +1271,10 @@ __global__ void __launch_bounds__(kDecThreads, 2) decode_batch_kernel(DecBatchAr
                 g = __shfl_sync(0xffffffffu, next, 0);
             }
         }
+        HB_PHASE_MARK(5);  // image -> global memory
     }
-    // the last tile this block decoded is still in its slot
-    if (pend) {
-        if (warp == 0) {
-            const uint64_t prefix = lookback_resolve(a.tile_state, pend_tile, pend_total);
-            if (lane == 0) s_prefix = prefix;
-        }
-        __syncthreads();
-        dec_flush_tile(b, slot, s_prefix, pend_total, pend_item0, pend_nitems, s_off[(iter & 1u) ^ 1u]);
-    }
+    if (tid == 0) s_hand_tile[hand & 1] = kDecDone;
+    dec_bar_arrive(5 * team + 2 + (hand & 1));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1263,6 +1581,8 @@ struct StreamFusedArgs {
     uint64_t *tile_rec;      // per tile: [15:0] entry of its first chunk, [31:16] exit of its last, [33:32] term of its
                              // last, [63] published
     uint32_t *fail;
+    const uint2 *lut2;       // 64-bit entries of the lean step (decode_span_lean)
+    uint32_t lut2_count, lut2_trap;
     uint32_t num_tiles;
     uint32_t row_words;      // row stride in words (odd)
     uint8_t *scratch;        // deferred output: one slot of scratch_slot bytes per block (16-byte aligned)
@@ -1296,9 +1616,9 @@ __device__ __forceinline__ void stream_flush_tile(
 }
 
 __global__ void __launch_bounds__(kStreamThreads, 2) stream_fused_kernel(StreamFusedArgs f) {
-    extern __shared__ __align__(16) uint32_t s_lut[];  // [LUT][stage][rows]
+    extern __shared__ __align__(128) uint32_t s_lut[];  // [LUT2][stage][rows]
     const StreamArgs &a = f.s;
-    const uint32_t lut_pad = (a.lut_count + 3u) & ~3u;
+    const uint32_t lut_pad = 2u * f.lut2_count;
     uint32_t *s_in = s_lut + lut_pad;
     uint8_t *const s_dense = reinterpret_cast<uint8_t *>(s_in);
     constexpr uint32_t kStageBytes = (kStreamStageWords * 4 + 15u) & ~15u;
@@ -1311,7 +1631,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) stream_fused_kernel(StreamF
     __shared__ uint64_t s_prefix, s_last_cbits;
     __shared__ uint32_t s_tile, s_first_term, s_total, s_last_rel, s_last_term;
 
-    for (uint32_t i = threadIdx.x; i < a.lut_count; i += kStreamThreads) s_lut[i] = a.lut[i];
+    const Lut2 lut2 = lut2_load(reinterpret_cast<uint2 *>(s_lut), f.lut2, f.lut2_count, a.root_bits, f.lut2_trap);
     const uint32_t k = threadIdx.x, lane = lane_id(), warp = threadIdx.x >> 5;
     const uint32_t row_addr = (uint32_t)__cvta_generic_to_shared(s_rows) + k * row_bytes;
     uint8_t *const slot = f.scratch + (size_t)blockIdx.x * f.scratch_slot;  // this block's deferred-output slot
@@ -1347,11 +1667,11 @@ __global__ void __launch_bounds__(kStreamThreads, 2) stream_fused_kernel(StreamF
                 entry = (uint32_t)(a.begin_bit - begin);
             } else {
                 const uint64_t from = max(begin - kPrerollBits, a.begin_bit);
-                const SpanS pre = decode_span_smem<false, true, true>(
-                    s_in, s_lut, a.root_bits, (uint32_t)(from - origin), s_begin, s_end, 0u);
+                const SpanS pre = decode_span_lean<false, true, true>(
+                    s_in, lut2, a.root_bits, (uint32_t)(from - origin), s_begin, s_end, 0u);
                 entry = pre.pos >= s_begin ? pre.pos - s_begin : 0u;
             }
-            const SpanS r = decode_span_smem<true, true, false>(s_in, s_lut, a.root_bits, s_begin + entry, s_stop, s_end, row_addr);
+            const SpanS r = decode_span_lean<true, true, false>(s_in, lut2, a.root_bits, s_begin + entry, s_stop, s_end, row_addr);
             exit = r.term == kTermStop ? r.pos - s_stop : 0u;
             nsym = r.nsym;
             term = r.term;
@@ -1366,7 +1686,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) stream_fused_kernel(StreamF
             const bool redo = valid && lane > 0 && !exact && prev_term == kTermStop && entry != prev_exit;
             if (!__any_sync(0xffffffffu, redo)) break;
             if (redo) {
-                const SpanS r = decode_span_smem<true, true, false>(s_in, s_lut, a.root_bits, s_begin + prev_exit, s_stop, s_end, row_addr);
+                const SpanS r = decode_span_lean<true, true, false>(s_in, lut2, a.root_bits, s_begin + prev_exit, s_stop, s_end, row_addr);
                 entry = prev_exit;
                 exit = r.term == kTermStop ? r.pos - s_stop : 0u;
                 nsym = r.nsym;
@@ -1400,7 +1720,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) stream_fused_kernel(StreamF
                 }
                 if (!__syncthreads_or(redo)) break;
                 if (redo) {
-                    const SpanS r = decode_span_smem<true, true, false>(s_in, s_lut, a.root_bits, s_begin + want, s_stop, s_end, row_addr);
+                    const SpanS r = decode_span_lean<true, true, false>(s_in, lut2, a.root_bits, s_begin + want, s_stop, s_end, row_addr);
                     s_entry[k] = (uint16_t)want;
                     s_exit[k] = (uint16_t)(r.term == kTermStop ? r.pos - s_stop : 0u);
                     s_nsym[k] = r.nsym;

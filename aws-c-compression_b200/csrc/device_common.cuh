@@ -6,6 +6,16 @@
 
 namespace hb {
 
+#ifdef HB_PHASE_TIMING
+__device__ unsigned long long hb_phase_cycles[16];  // (development builds: tools/phase_probe.py)
+__device__ unsigned long long hb_tile_times[4][8192];  // per tile: ticket, publish, resolve start, resolve end (globaltimer ns)
+__device__ __forceinline__ unsigned long long hb_now_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#endif
+
 // Error values written to per-item status arrays (match aws-c-common / compression.h).
 constexpr int32_t kStatusOk = 0;
 constexpr int32_t kStatusShortBuffer = 4;       // AWS_ERROR_SHORT_BUFFER
@@ -195,9 +205,15 @@ __device__ __forceinline__ uint64_t lookback_resolve(uint64_t *tile_state, uint3
         const uint32_t pmask = __ballot_sync(0xffffffffu, found);
         const uint32_t first = pmask ? (uint32_t)(__ffs(pmask) - 1) : 32u;
         if (__any_sync(0xffffffffu, missing && lane <= first)) {
+#ifdef HB_PHASE_TIMING
+            if (lane == 0) atomicAdd(&hb_phase_cycles[9], 1ull);
+#endif
             __nanosleep(100);
             continue;
         }
+#ifdef HB_PHASE_TIMING
+        if (lane == 0) atomicAdd(&hb_phase_cycles[10], 1ull);
+#endif
         uint64_t contrib = lane <= first ? sum : 0;
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
@@ -208,6 +224,57 @@ __device__ __forceinline__ uint64_t lookback_resolve(uint64_t *tile_state, uint3
     }
     if (lane == 0)
         st_relaxed_u64(&tile_state[tile], (kLbPrefix << kLbFlagShift) | ((exclusive + aggregate) & kLbValueMask));
+    return exclusive;
+}
+
+// One full warp: the exclusive prefix of `tile` alone — the sum over its predecessors, which does not depend on
+// the tile's own aggregate, so it can be started as soon as the tile is TAKEN and runs next to the tile's own work.
+// Nothing is published (the caller stores the inclusive prefix once it knows both halves).
+__device__ __forceinline__ uint64_t lookback_exclusive(uint64_t *tile_state, uint32_t tile) {
+    const uint32_t lane = lane_id();
+    if (tile == 0) return 0;
+    uint64_t exclusive = 0;
+    int64_t gtop = ((int64_t)tile - 1) >> 2;
+    uint32_t rtop = (tile - 1) & 3;
+    while (true) {
+        const int64_t g = gtop - (int64_t)lane;
+        uint64_t word[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) word[e] = kLbPrefix << kLbFlagShift;
+        if (g >= 0)
+            asm volatile("ld.relaxed.gpu.global.v4.b64 {%0, %1, %2, %3}, [%4];"
+                         : "=l"(word[0]), "=l"(word[1]), "=l"(word[2]), "=l"(word[3])
+                         : "l"(tile_state + 4 * g)
+                         : "memory");
+        const uint32_t last = lane == 0 ? rtop : 3u;
+        uint64_t sum = 0;
+        bool found = false, missing = false;
+#pragma unroll
+        for (int e = 3; e >= 0; --e) {
+            if ((uint32_t)e <= last && !found && !missing) {
+                const uint64_t status = word[e] >> kLbFlagShift;
+                if (status == kLbInvalid) {
+                    missing = true;
+                } else {
+                    sum += word[e] & kLbValueMask;
+                    found = status == kLbPrefix;
+                }
+            }
+        }
+        const uint32_t pmask = __ballot_sync(0xffffffffu, found);
+        const uint32_t first = pmask ? (uint32_t)(__ffs(pmask) - 1) : 32u;
+        if (__any_sync(0xffffffffu, missing && lane <= first)) {
+            __nanosleep(400);  // (the predecessors are still decoding: this runs next to the tile's own work)
+            continue;
+        }
+        uint64_t contrib = lane <= first ? sum : 0;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
+        exclusive += contrib;
+        if (pmask) break;
+        gtop -= 32;
+        rtop = 3;
+    }
     return exclusive;
 }
 

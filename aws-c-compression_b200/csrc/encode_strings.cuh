@@ -231,7 +231,6 @@ __global__ void __launch_bounds__(kBitsThreads, 4) str_bits_kernel(const uint2 *
                 v[i] = make_uint4(w[0], w[1], w[2], w[3]);
             }
         }
-        uint32_t tot[kBitsVecsPerThread];
 #pragma unroll
         for (int i = 0; i < kBitsVecsPerThread; ++i) {
             const uint32_t vi = i * kBitsThreads + tid;
@@ -248,7 +247,6 @@ __global__ void __launch_bounds__(kBitsThreads, 4) str_bits_kernel(const uint2 *
             }
             *reinterpret_cast<uint4 *>(&s_pre[vi][0]) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             *reinterpret_cast<uint4 *>(&s_pre[vi][4]) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-            tot[i] = run;
             s_vex[vi] = run;  // (raw totals first; scanned below)
         }
         __syncthreads();
@@ -273,7 +271,6 @@ __global__ void __launch_bounds__(kBitsThreads, 4) str_bits_kernel(const uint2 *
         }
         if (tid == kBitsThreads - 1) s_vex[kBitsTileVecs] = run;
         __syncthreads();
-        (void)tot;
         // the strings that start in this tile, and the one that continues into it
         const uint32_t f0 = a.bits_tile_first[tile], f1 = a.bits_tile_first[tile + 1];
         if (tid == 0 && f0 > 0) {

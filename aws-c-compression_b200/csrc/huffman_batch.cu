@@ -117,6 +117,8 @@ struct aws_huffman_batch_ctx {
     hb::DeviceTables tables{};
     uint2 *d_enc = nullptr;
     uint32_t *d_lut = nullptr;
+    uint2 *d_lut2 = nullptr;  // 64-bit entries of the lean decode step (decode_fast.cuh)
+    uint32_t lut2_count = 0, lut2_trap = 0;
     uint32_t lut_smem_entries = 0;
     uint64_t launches = 0;
 
@@ -444,15 +446,18 @@ int decode_batch_fast(
     DecBatchArgs a{};
     a.b = v;
     a.lut = ctx->tables.lut;
-    a.lut_count = ctx->tables.lut_count;
+    a.lut2 = ctx->d_lut2;
+    a.lut2_count = ctx->lut2_count;
+    a.lut2_trap = ctx->lut2_trap;
     a.root_bits = ctx->tables.lut_root_bits;
     a.min_len = std::max<uint32_t>(1, ctx->tables.min_len);
     // Shared memory of one block (two blocks per SM): [LUT][stage][rows]. A string of L bytes decodes to at
     // most 8 L / min_len symbols, so the row area is that much larger than the stage; and the dense output
     // image (which reuses the stage and the front of the rows) must end before row offset `front`
     // (decode_batch_kernel step 4): rows <= stage + front - 32.
-    const size_t lut_bytes = (((size_t)a.lut_count + 3) & ~size_t(3)) * 4;
-    const size_t budget = (size_t)108 * 1024 - 6 * 1024 /* static */ - lut_bytes;
+    const size_t lut_bytes = (size_t)a.lut2_count * 8;
+    // one block per SM: [LUT2][team 0: stage, rows][team 1: stage, rows] + the teams' static arrays
+    const size_t budget = ((size_t)224 * 1024 - lut_bytes) / kDecTeams - 10 * 1024 /* static */;
     const double expand = 8.0 / a.min_len;
     size_t stage_bytes = (size_t)((double)budget / (1.0 + expand)) & ~size_t(15);
     stage_bytes = std::max<size_t>(stage_bytes, 2 * kDecMaxRow);
@@ -461,12 +466,13 @@ int decode_batch_fast(
     rows_bytes = std::min(rows_bytes, stage_bytes + front - 64) & ~size_t(15);
     a.stage_words = (uint32_t)(stage_bytes / 4 - 2);
     a.rows_bytes = (uint32_t)rows_bytes;
-    // strings per tile: as many as fit the stage and the row area at the batch's average length (with 12 % to
-    // spare for tiles above the average), in whole warps
+    // strings per tile: as many as fit the stage and the row area at the batch's average length, in whole warps,
+    // with 20 % to spare for tiles above the average (a tile that does not fit takes the two-pass global route
+    // and every tile behind it waits for its count: at 12 % two tiles in 4,500 overflowed on the benchmark)
     {
         const double avg = std::max(1.0, (double)total_in / (double)v.n);
-        const double by_stage = (double)(stage_bytes - 64) / (1.12 * avg);
-        const double by_rows = (double)rows_bytes / (1.12 * avg * expand + kDecRowSlack);
+        const double by_stage = (double)(stage_bytes - 64) / (1.2 * avg);
+        const double by_rows = (double)rows_bytes / (1.2 * avg * expand + kDecRowSlack);
         const uint64_t fit = (uint64_t)std::max(32.0, std::min(by_stage, by_rows));
         a.items_per_tile = (uint32_t)std::min<uint64_t>(kDecItemsPerTile, fit & ~uint64_t(31));
     }
@@ -477,17 +483,13 @@ int decode_batch_fast(
     a.tile_state = sc.tile_state.as<uint64_t>();
     a.ticket = reinterpret_cast<uint32_t *>(a.tile_state + num_tiles);
     a.num_tiles = (uint32_t)num_tiles;
-    const size_t smem = lut_bytes + ((stage_bytes + 15) & ~size_t(15)) + rows_bytes + 64;
+    const size_t team_bytes = ((stage_bytes + 15) & ~size_t(15)) + rows_bytes + 64;
+    const size_t smem = lut_bytes + kDecTeams * team_bytes;
     HB_CUDA_TRY(cudaFuncSetAttribute(
         framed ? decode_batch_kernel<true> : decode_batch_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const unsigned blocks = (unsigned)std::min<uint64_t>(num_tiles, (uint64_t)ctx->sm_count * 2);
-    // deferred output: a block parks the dense image of a tile (never larger than its shared memory) in its own
-    // slot until the next tile is decoded
-    a.scratch_slot = (uint32_t)((smem + 64 + 255) & ~size_t(255));
-    HB_CUDA_TRY(sc.deferred.reserve((size_t)blocks * a.scratch_slot));
-    a.scratch = sc.deferred.as<uint8_t>();
-    if (framed) decode_batch_kernel<true><<<blocks, kDecThreads, smem, stream>>>(a);
-    else decode_batch_kernel<false><<<blocks, kDecThreads, smem, stream>>>(a);
+    const unsigned blocks = (unsigned)std::min<uint64_t>((num_tiles + kDecTeams - 1) / kDecTeams, (uint64_t)ctx->sm_count);
+    if (framed) decode_batch_kernel<true><<<blocks, kDecTeams * kDecBlock, smem, stream>>>(a);
+    else decode_batch_kernel<false><<<blocks, kDecTeams * kDecBlock, smem, stream>>>(a);
     ++ctx->launches;
     HB_CUDA_TRY(cudaGetLastError());
     return AWS_OP_SUCCESS;
@@ -522,7 +524,7 @@ int decode_stream_fast(
     // ---- fused single pass ------------------------------------------------------------------------------------
     const uint32_t min_len = std::max<uint32_t>(1, ctx->tables.min_len);
     const uint32_t row_words = (((kChunkBits + 31) / min_len + 4 + 3) / 4) | 1u;
-    const size_t lut_bytes = (((size_t)ctx->tables.lut_count + 3) & ~size_t(3)) * 4;
+    const size_t lut_bytes = (size_t)ctx->lut2_count * 8;
     const size_t stage_bytes = (kStreamStageWords * 4 + 15) & ~size_t(15);
     const size_t fused_smem = lut_bytes + stage_bytes + (size_t)kStreamThreads * row_words * 4 + 16;
     // (the dense output image reuses the stage and the front of the rows: stream_fused_kernel step 5)
@@ -535,6 +537,9 @@ int decode_stream_fast(
         f.b = v;
         f.num_tiles = (uint32_t)((f.s.num_chunks + kStreamThreads - 1) / kStreamThreads);
         f.row_words = row_words;
+        f.lut2 = ctx->d_lut2;
+        f.lut2_count = ctx->lut2_count;
+        f.lut2_trap = ctx->lut2_trap;
         // [tile_state: num_tiles][tile_rec: num_tiles][ticket][fail]
         const size_t words = 2 * (size_t)f.num_tiles + 2;
         HB_CUDA_TRY(sc.fused.reserve(words * sizeof(uint64_t)));
@@ -1314,6 +1319,47 @@ static int hb_ctx_from_codes(
                          (len1 << 2) | 2u;
         }
         HB_CTX_TRY(cudaMemcpy(ctx->d_lut, dev.data(), (size_t)lut.count * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        // LUT2 (decode_span_lean): the same tables as 64-bit entries {symbols, count | bits consumed, next table};
+        // tables are 32-byte aligned (the step takes the table address and the index shift out of one word)
+        std::vector<uint2> lut2;
+        const uint32_t root_y = 32u - lut.root_bits;  // next step: root table (offset 0)
+        lut2.resize((size_t)1 << lut.root_bits);
+        while (lut2.size() & 3) lut2.push_back(uint2{0, 0});
+        const uint32_t trap_base = (uint32_t)lut2.size();
+        const uint32_t trap_y = (trap_base * 8u) | 31u;  // index width 1, nothing consumed: a trapped lane stays
+        for (int i = 0; i < 4; ++i) lut2.push_back(uint2{0, trap_y});
+        struct Conv {
+            std::vector<uint2> &out;
+            const std::vector<uint32_t> &dev;
+            uint32_t root_y, trap_y;
+            void table(uint32_t new_base, uint32_t old_base, uint32_t width, uint32_t used) {
+                for (uint32_t idx = 0; idx < (1u << width); ++idx) {
+                    const uint32_t e = dev[old_base + idx];
+                    uint2 o;
+                    if (e == 0) {
+                        o = uint2{0, trap_y};
+                    } else if (e >= 0x01000000u) {
+                        const uint32_t total = e >> 24, len1 = (e >> 2) & 63u, cnt = e & 3u;
+                        o.x = ((e >> 8) & 0xffu) | (((e >> 16) & 0xffu) << 8) | (len1 << 16) | (cnt << 30);
+                        o.y = root_y | ((total - used) << 24);
+                    } else {
+                        const uint32_t w2 = (e >> 20) & 0xfu, b2 = e & 0xFFFFFu;
+                        size_t child = (out.size() + 3) & ~size_t(3);
+                        out.resize(child + std::max<size_t>(4, (size_t)1 << w2), uint2{0, trap_y});
+                        table((uint32_t)child, b2, w2, used + width);
+                        o.x = 0;
+                        o.y = ((uint32_t)child * 8u) | (32u - w2) | (width << 24);
+                    }
+                    out[new_base + idx] = o;
+                }
+            }
+        } conv{lut2, dev, root_y, trap_y};
+        conv.table(0, 0, lut.root_bits, 0);
+        while (lut2.size() & 3) lut2.push_back(uint2{0, trap_y});
+        ctx->lut2_count = (uint32_t)lut2.size();
+        ctx->lut2_trap = trap_base;
+        HB_CTX_TRY(cudaMalloc(&ctx->d_lut2, lut2.size() * sizeof(uint2)));
+        HB_CTX_TRY(cudaMemcpy(ctx->d_lut2, lut2.data(), lut2.size() * sizeof(uint2), cudaMemcpyHostToDevice));
     }
     {
         int sms = 0;
@@ -1348,6 +1394,7 @@ void aws_huffman_batch_ctx_destroy(struct aws_huffman_batch_ctx *ctx) {
     }
     if (ctx->d_enc) cudaFree(ctx->d_enc);
     if (ctx->d_lut) cudaFree(ctx->d_lut);
+    if (ctx->d_lut2) cudaFree(ctx->d_lut2);
     GrowBuf *bufs[] = {&ctx->s_in,       &ctx->s_in_off,      &ctx->s_out,      &ctx->s_out_off,
                        &ctx->s_caps,     &ctx->s_status,      &ctx->s_consumed, &ctx->s_ovf_pattern,
                        &ctx->s_ovf_bits, &ctx->s_left_bits,   &ctx->s_left_num, &ctx->hp_pay,
@@ -1574,3 +1621,18 @@ int aws_huffman_batch_concat_offsets(
 }
 
 }  // extern "C"
+
+#ifdef HB_PHASE_TIMING
+// development builds only (tools/phase_probe.py): cycles per phase of decode_batch_kernel, summed over blocks
+extern "C" int aws_huffman_batch_debug_phase_cycles(unsigned long long *out16, int reset) {
+    if (cudaMemcpyFromSymbol(out16, hb::hb_phase_cycles, 16 * sizeof(unsigned long long)) != cudaSuccess) return -1;
+    if (reset) {
+        unsigned long long zero[16] = {0};
+        if (cudaMemcpyToSymbol(hb::hb_phase_cycles, zero, sizeof(zero)) != cudaSuccess) return -1;
+    }
+    return 0;
+}
+extern "C" int aws_huffman_batch_debug_tile_times(unsigned long long *out /* 4 x 8192 */) {
+    return cudaMemcpyFromSymbol(out, hb::hb_tile_times, sizeof(unsigned long long) * 4 * 8192) == cudaSuccess ? 0 : -1;
+}
+#endif
