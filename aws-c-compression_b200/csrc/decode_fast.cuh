@@ -649,7 +649,14 @@ __device__ __forceinline__ SpanS decode_span_lean(
         uint32_t ns = t.root_ns, tb = t.addr;
         const uint32_t root_tb = t.addr;
         uint32_t acc = 0;  // (kEmit) symbols not stored yet: the low out_addr & 3 bytes
+#ifdef HB_PHASE_TIMING
+        const long long tl0 = clock64();
+        uint32_t rounds = 0;
+#endif
         while (pos < pair_end || tb != root_tb) {
+#ifdef HB_PHASE_TIMING
+            ++rounds;
+#endif
 #pragma unroll
             for (int step = 0; step < kUnifiedSteps; ++step) {
                 if (kEmit) {
@@ -725,6 +732,15 @@ __device__ __forceinline__ SpanS decode_span_lean(
                 tb = root_tb;
             }
         }
+#ifdef HB_PHASE_TIMING
+        {   // the lane of the warp that ran longest: its rounds and the cycles the warp spent in the loop
+            const uint32_t mx = __reduce_max_sync(__activemask(), rounds);
+            if (rounds == mx && mx > 0 && kEmit && !kPadded) {
+                atomicAdd(&hb_phase_cycles[14], (unsigned long long)(clock64() - tl0));
+                atomicAdd(&hb_phase_cycles[15], (unsigned long long)mx);
+            }
+        }
+#endif
         if (pos & kParked) {
             pos = pos0;
             out_addr = out0;
@@ -828,10 +844,23 @@ __device__ __forceinline__ DecodeSpan decode_span_lut2(
 #define HB_PHASE_MARK(i) do { } while (0)
 #endif
 
-constexpr int kDecThreads = 256;
+#ifndef HB_DEC_THREADS
+#define HB_DEC_THREADS 256
+#endif
+#ifndef HB_DEC_TEAMS
+#define HB_DEC_TEAMS 2
+#endif
+constexpr int kDecThreads = HB_DEC_THREADS;  // worker threads of a team
 constexpr int kDecWarps = kDecThreads / 32;
 constexpr int kDecBlock = kDecThreads + 32;  // a team: 8 worker warps + 1 scout warp
-constexpr int kDecTeams = 2;                 // teams per block (they share the decode table)
+constexpr int kDecTeams = HB_DEC_TEAMS;      // teams per block (they share the decode table); 5 named barriers each
+// Warps of a team that decode (the others wait at the barrier behind the decode phase, which costs nothing). The
+// phase cannot end before the tile's longest string does, so more lanes than the work needs only add contention
+// to every step of that string: the warps pull groups of 32 strings, longest first.
+#ifndef HB_DEC_PULL_WARPS
+#define HB_DEC_PULL_WARPS (HB_DEC_THREADS / 32)
+#endif
+constexpr int kDecPullWarps = HB_DEC_PULL_WARPS;
 constexpr uint32_t kDecDone = 0xffffffffu;
 constexpr int kDecItemsPerTile = 288;        // strings per tile (9 groups of 32)
 // Named barriers (as in encode_tiled.cuh). Workers among themselves: 1. Hand-off of a tile to the scout: 2 + parity
@@ -1025,7 +1054,7 @@ __global__ void __launch_bounds__(kDecTeams * kDecBlock, 1) decode_batch_kernel(
         dec_worker_sync(team);  // previous tile fully done (and the LUT is in place on the first trip)
         if (tid == 0) {
             s_tile = atomicAdd(a.ticket, 1u);
-            s_next = kDecWarps;
+            s_next = kDecPullWarps;
             s_fits = 1;
         }
         for (uint32_t i = tid; i < 256; i += kDecThreads) s_hist[i] = 0;
@@ -1114,7 +1143,7 @@ __global__ void __launch_bounds__(kDecTeams * kDecBlock, 1) decode_batch_kernel(
 
         HB_PHASE_MARK(0);  // ticket, string table, staging, sort
         // ---- decode (staged: once, into the rows; otherwise: count) ------------------------------------------
-        for (uint32_t g = warp; g < ngroups;) {
+        for (uint32_t g = warp < (uint32_t)kDecPullWarps ? warp : ngroups; g < ngroups;) {
             const uint32_t slot = g * 32 + lane;
             if (slot < nitems) {
                 const uint32_t it = s_perm[slot];
@@ -1350,7 +1379,7 @@ __device__ __forceinline__ uint32_t stream_be_word(uint32_t raw, int64_t w, uint
     return v;
 }
 
-__device__ __forceinline__ void stream_stage(const StreamArgs &a, uint64_t c0, uint32_t *s_in) {
+__device__ __forceinline__ void stream_stage(const StreamArgs &a, uint64_t c0, uint32_t *s_in, uint32_t tid) {
     const uint4 *g4 = reinterpret_cast<const uint4 *>(a.in_aligned);
     const uint64_t end_byte = a.end_bit >> 3;
     const uint64_t nquads_valid = (end_byte + 15) >> 4;
@@ -1359,7 +1388,7 @@ __device__ __forceinline__ void stream_stage(const StreamArgs &a, uint64_t c0, u
     if (c0 >= 1 && ((c0 - 1) * 8 + kQuads) * 16 <= end_byte) {
         // interior tile: every staged byte belongs to the stream
         const uint4 *src = g4 + (c0 - 1) * 8;
-        for (uint32_t i = threadIdx.x; i < kQuads; i += kStreamThreads) {
+        for (uint32_t i = tid; i < kQuads; i += kStreamThreads) {
             const uint32_t row = i >> 3, col4 = i & 7;
             const uint4 raw = __ldg(src + i);
             const uint32_t v0 = __byte_perm(raw.x, 0, 0x0123);
@@ -1374,7 +1403,7 @@ __device__ __forceinline__ void stream_stage(const StreamArgs &a, uint64_t c0, u
         }
         return;
     }
-    for (uint32_t i = threadIdx.x; i < kQuads; i += kStreamThreads) {
+    for (uint32_t i = tid; i < kQuads; i += kStreamThreads) {
         const uint32_t row = i >> 3, col4 = i & 7;
         const int64_t q = ((int64_t)c0 - 1 + row) * 8 + col4;  // aligned 16-byte index in the stream
         uint4 raw = make_uint4(0, 0, 0, 0);
@@ -1402,7 +1431,7 @@ __global__ void __launch_bounds__(kStreamThreads) stream_sync_kernel(StreamArgs 
     for (uint64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const uint64_t c0 = t * kStreamThreads;
         __syncthreads();
-        stream_stage(a, c0, s_in);
+        stream_stage(a, c0, s_in, threadIdx.x);
         __syncthreads();
         const uint64_t k = c0 + threadIdx.x;
         if (k >= a.num_chunks) continue;
@@ -1519,7 +1548,7 @@ __global__ void __launch_bounds__(kStreamThreads) stream_write_kernel(StreamArgs
     for (uint64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const uint64_t c0 = t * kStreamThreads;
         __syncthreads();
-        stream_stage(a, c0, s_in);
+        stream_stage(a, c0, s_in, threadIdx.x);
         __syncthreads();
         const uint64_t k = c0 + threadIdx.x;
         if (k > last) continue;
@@ -1596,11 +1625,11 @@ __device__ __forceinline__ uint64_t fused_chunk_stop(const StreamArgs &a, uint64
 // Whole block: the tile whose dense image sits in `slot` goes to its final place, `tile_base` being known now;
 // the tile of the stream's last chunk also carries the item-level results.
 __device__ __forceinline__ void stream_flush_tile(
-    const StreamFusedArgs &f, const uint8_t *slot, uint64_t tile_base, uint32_t total, bool last_tile, uint32_t last_rel,
+    uint32_t tid, const StreamFusedArgs &f, const uint8_t *slot, uint64_t tile_base, uint32_t total, bool last_tile, uint32_t last_rel,
     uint64_t cbits, uint32_t my_term) {
     const BatchView &b = f.b;
     const StreamArgs &a = f.s;
-    if (last_tile && threadIdx.x == 0) {
+    if (last_tile && tid == 0) {
         const uint64_t nsym = tile_base + last_rel;
         b.out_offsets[0] = 0;
         b.out_offsets[1] = nsym;
@@ -1612,44 +1641,73 @@ __device__ __forceinline__ void stream_flush_tile(
     }
     const uint64_t room = tile_base < b.out_capacity ? b.out_capacity - tile_base : 0;
     const uint32_t ncopy = (uint32_t)min((uint64_t)total, room);
-    block_copy_realign(slot, b.out + tile_base, ncopy, threadIdx.x, blockDim.x);
+    block_copy_realign(slot, b.out + tile_base, ncopy, tid, kStreamThreads);
 }
 
-__global__ void __launch_bounds__(kStreamThreads, 2) stream_fused_kernel(StreamFusedArgs f) {
-    extern __shared__ __align__(128) uint32_t s_lut[];  // [LUT2][stage][rows]
+// Shared state of one team of stream_fused_kernel (the two teams of a block share one copy of the decode table,
+// see decode_batch_kernel).
+struct StreamTeamShared {
+    uint16_t entry[kStreamThreads], exit[kStreamThreads];
+    uint32_t nsym[kStreamThreads];
+    uint8_t term[kStreamThreads];
+    uint32_t warp_sum[kStreamThreads / 32];
+    uint64_t prefix, last_cbits;
+    uint32_t tile, first_term, total, last_rel, last_term, flag;
+};
+constexpr int kStreamTeams = 2;
+// team barriers: 1 + team (plain), and the OR-reduction of a predicate over the team
+__device__ __forceinline__ void stream_team_sync(uint32_t team) { asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "n"(kStreamThreads) : "memory"); }
+__device__ __forceinline__ bool stream_team_or(uint32_t team, bool pred) {
+    uint32_t out;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 p, %1, 0;\n\tbarrier.red.or.pred q, %2, %3, p;\n\tselp.u32 %0, 1, 0, q;\n\t}"
+        : "=r"(out)
+        : "r"((uint32_t)pred), "r"(1 + team), "n"(kStreamThreads)
+        : "memory");
+    return out != 0;
+}
+
+__global__ void __launch_bounds__(kStreamTeams * kStreamThreads, 1) stream_fused_kernel(StreamFusedArgs f) {
+    extern __shared__ __align__(128) uint32_t s_lut[];  // [LUT2][team 0: stage, rows][team 1: stage, rows]
+    __shared__ StreamTeamShared s_teams[kStreamTeams];
     const StreamArgs &a = f.s;
+    const uint32_t team = threadIdx.x / kStreamThreads, tid = threadIdx.x - team * kStreamThreads;
+    StreamTeamShared &sh = s_teams[team];
+    uint16_t (&s_entry)[kStreamThreads] = sh.entry, (&s_exit)[kStreamThreads] = sh.exit;
+    uint32_t (&s_nsym)[kStreamThreads] = sh.nsym;
+    uint8_t (&s_term)[kStreamThreads] = sh.term;
+    uint32_t (&s_warp_sum)[kStreamThreads / 32] = sh.warp_sum;
+    uint64_t &s_prefix = sh.prefix, &s_last_cbits = sh.last_cbits;
+    uint32_t &s_tile = sh.tile, &s_first_term = sh.first_term, &s_total = sh.total, &s_last_rel = sh.last_rel,
+             &s_last_term = sh.last_term;
     const uint32_t lut_pad = 2u * f.lut2_count;
-    uint32_t *s_in = s_lut + lut_pad;
-    uint8_t *const s_dense = reinterpret_cast<uint8_t *>(s_in);
     constexpr uint32_t kStageBytes = (kStreamStageWords * 4 + 15u) & ~15u;
-    uint8_t *const s_rows = s_dense + kStageBytes;
     const uint32_t row_bytes = f.row_words * 4;
-    __shared__ uint16_t s_entry[kStreamThreads], s_exit[kStreamThreads];
-    __shared__ uint32_t s_nsym[kStreamThreads];
-    __shared__ uint8_t s_term[kStreamThreads];
-    __shared__ uint32_t s_warp_sum[kStreamThreads / 32];
-    __shared__ uint64_t s_prefix, s_last_cbits;
-    __shared__ uint32_t s_tile, s_first_term, s_total, s_last_rel, s_last_term;
+    const uint32_t team_bytes = (kStageBytes + kStreamThreads * row_bytes + 16u + 15u) & ~15u;
+    uint32_t *s_in = s_lut + lut_pad + team * (team_bytes / 4);
+    uint8_t *const s_dense = reinterpret_cast<uint8_t *>(s_in);
+    uint8_t *const s_rows = s_dense + kStageBytes;
 
     const Lut2 lut2 = lut2_load(reinterpret_cast<uint2 *>(s_lut), f.lut2, f.lut2_count, a.root_bits, f.lut2_trap);
-    const uint32_t k = threadIdx.x, lane = lane_id(), warp = threadIdx.x >> 5;
+    __syncthreads();  // the LUT is in place
+    const uint32_t k = tid, lane = lane_id(), warp = tid >> 5;
     const uint32_t row_addr = (uint32_t)__cvta_generic_to_shared(s_rows) + k * row_bytes;
-    uint8_t *const slot = f.scratch + (size_t)blockIdx.x * f.scratch_slot;  // this block's deferred-output slot
+    uint8_t *const slot = f.scratch + ((size_t)blockIdx.x * kStreamTeams + team) * f.scratch_slot;  // this block's deferred-output slot
     bool pend = false;  // a tile's image sits in the slot (block-uniform)
     uint32_t pend_tile = 0, pend_total = 0;
 
     while (true) {
-        __syncthreads();  // previous tile fully done (and the LUT is in place on the first trip)
+        stream_team_sync(team);  // previous tile fully done (and the LUT is in place on the first trip)
         if (k == 0) {
             s_tile = atomicAdd(f.ticket, 1u);
             s_first_term = kStreamThreads;
         }
-        __syncthreads();
+        stream_team_sync(team);
         const uint32_t tile = s_tile;
         if (tile >= f.num_tiles) break;
         const uint64_t c0 = (uint64_t)tile * kStreamThreads;
-        stream_stage(a, c0, s_in);
-        __syncthreads();
+        stream_stage(a, c0, s_in, tid);
+        stream_team_sync(team);
 
         // ---- decode my chunk -------------------------------------------------------------------------------------
         const uint64_t chunk = c0 + k;
@@ -1698,7 +1756,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) stream_fused_kernel(StreamF
         s_exit[k] = (uint16_t)exit;
         s_nsym[k] = nsym;
         s_term[k] = (uint8_t)term;
-        __syncthreads();
+        stream_team_sync(team);
 
         // ---- make the tile consistent: in itself, then with the previous tile -----------------------------------
         const uint32_t nvalid = (uint32_t)min((uint64_t)kStreamThreads, a.num_chunks - c0);
@@ -1718,7 +1776,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) stream_fused_kernel(StreamF
                         want = prev_exit0;
                     }
                 }
-                if (!__syncthreads_or(redo)) break;
+                if (!stream_team_or(team, redo)) break;
                 if (redo) {
                     const SpanS r = decode_span_lean<true, true, false>(s_in, lut2, a.root_bits, s_begin + want, s_stop, s_end, row_addr);
                     s_entry[k] = (uint16_t)want;
@@ -1727,7 +1785,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) stream_fused_kernel(StreamF
                     s_term[k] = (uint8_t)r.term;
                     last_pos = r.pos;
                 }
-                __syncthreads();
+                stream_team_sync(team);
             }
             if (k == 0) {
                 const uint64_t rec = (1ull << 63) | (uint64_t)s_entry[0] | ((uint64_t)s_exit[nvalid - 1] << 16) |
@@ -1750,7 +1808,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) stream_fused_kernel(StreamF
             }
         }
         if (valid && s_term[k] != kTermStop) atomicMin(&s_first_term, k);
-        __syncthreads();
+        stream_team_sync(team);
         const uint32_t first_term = s_first_term;
         // something stopped before the stream's last chunk: not for this kernel
         if (first_term < kStreamThreads && c0 + first_term + 1 < a.num_chunks && k == 0) atomicExch(f.fail, 1u);
@@ -1759,7 +1817,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) stream_fused_kernel(StreamF
         const uint32_t cnt = (valid && k <= first_term) ? s_nsym[k] : 0u;
         const uint32_t incl = warp_inclusive_scan(cnt);
         if (lane == 31) s_warp_sum[warp] = incl;
-        __syncthreads();
+        stream_team_sync(team);
         if (warp == 0) {
             const uint32_t w = lane < kStreamThreads / 32 ? s_warp_sum[lane] : 0u;
             const uint32_t wi = warp_inclusive_scan(w);
@@ -1770,7 +1828,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) stream_fused_kernel(StreamF
                 s_total = total;
             }
         }
-        __syncthreads();  // everybody is done with the stage
+        stream_team_sync(team);  // everybody is done with the stage
         const uint32_t off = s_warp_sum[warp] + incl - cnt;
         const uint32_t total = s_total;
 
@@ -1797,12 +1855,12 @@ __global__ void __launch_bounds__(kStreamThreads, 2) stream_fused_kernel(StreamF
 #ifndef HB_ABL_NO_COPY
                 if ((row_off < front) == (phase == 0)) smem_copy_row(s_rows + row_off, s_dense + off, cnt);
 #endif
-                __syncthreads();
+                stream_team_sync(team);
             }
         }
         if (pend) {
-            stream_flush_tile(f, slot, s_prefix, pend_total, pend_tile == f.num_tiles - 1, s_last_rel, s_last_cbits, s_last_term);
-            __syncthreads();  // the slot is free again
+            stream_flush_tile(tid, f, slot, s_prefix, pend_total, pend_tile == f.num_tiles - 1, s_last_rel, s_last_cbits, s_last_term);
+            stream_team_sync(team);  // the slot is free again
         }
         {
             const uint32_t nvec = (total + 15u) >> 4;
@@ -1820,8 +1878,8 @@ __global__ void __launch_bounds__(kStreamThreads, 2) stream_fused_kernel(StreamF
             const uint64_t prefix = lookback_resolve(f.tile_state, pend_tile, pend_total);
             if (lane == 0) s_prefix = prefix;
         }
-        __syncthreads();
-        stream_flush_tile(f, slot, s_prefix, pend_total, pend_tile == f.num_tiles - 1, s_last_rel, s_last_cbits, s_last_term);
+        stream_team_sync(team);
+        stream_flush_tile(tid, f, slot, s_prefix, pend_total, pend_tile == f.num_tiles - 1, s_last_rel, s_last_cbits, s_last_term);
     }
 }
 

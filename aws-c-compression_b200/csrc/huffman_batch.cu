@@ -457,7 +457,7 @@ int decode_batch_fast(
     // (decode_batch_kernel step 4): rows <= stage + front - 32.
     const size_t lut_bytes = (size_t)a.lut2_count * 8;
     // one block per SM: [LUT2][team 0: stage, rows][team 1: stage, rows] + the teams' static arrays
-    const size_t budget = ((size_t)224 * 1024 - lut_bytes) / kDecTeams - 10 * 1024 /* static */;
+    const size_t budget = ((size_t)224 * 1024 - lut_bytes) / kDecTeams - 9 * 1024 /* static */;
     const double expand = 8.0 / a.min_len;
     size_t stage_bytes = (size_t)((double)budget / (1.0 + expand)) & ~size_t(15);
     stage_bytes = std::max<size_t>(stage_bytes, 2 * kDecMaxRow);
@@ -526,10 +526,11 @@ int decode_stream_fast(
     const uint32_t row_words = (((kChunkBits + 31) / min_len + 4 + 3) / 4) | 1u;
     const size_t lut_bytes = (size_t)ctx->lut2_count * 8;
     const size_t stage_bytes = (kStreamStageWords * 4 + 15) & ~size_t(15);
-    const size_t fused_smem = lut_bytes + stage_bytes + (size_t)kStreamThreads * row_words * 4 + 16;
+    const size_t team_bytes = (stage_bytes + (size_t)kStreamThreads * row_words * 4 + 16 + 15) & ~size_t(15);
+    const size_t fused_smem = lut_bytes + kStreamTeams * team_bytes;  // one block per SM, two teams, one table
     // (the dense output image reuses the stage and the front of the rows: stream_fused_kernel step 5)
     const bool fused = (size_t)kStreamThreads * row_words * 4 + 16 <= 2 * stage_bytes - row_words * 4 - 32 &&
-                       fused_smem <= 110 * 1024 && !ctx->no_fused_stream;
+                       fused_smem <= 220 * 1024 && !ctx->no_fused_stream;
     if (fused) {
         StreamFusedArgs f{};
         f.s = a;
@@ -550,11 +551,11 @@ int decode_stream_fast(
         f.fail = f.ticket + 2;
         a.gate = f.fail;
         HB_CUDA_TRY(cudaFuncSetAttribute(stream_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem));
-        const unsigned blocks = (unsigned)std::min<uint64_t>(f.num_tiles, (uint64_t)ctx->sm_count * 2);
-        f.scratch_slot = (uint32_t)((fused_smem + 64 + 255) & ~size_t(255));
-        HB_CUDA_TRY(sc.deferred.reserve((size_t)blocks * f.scratch_slot));
+        const unsigned blocks = (unsigned)std::min<uint64_t>((f.num_tiles + kStreamTeams - 1) / kStreamTeams, (uint64_t)ctx->sm_count);
+        f.scratch_slot = (uint32_t)((team_bytes + 64 + 255) & ~size_t(255));
+        HB_CUDA_TRY(sc.deferred.reserve((size_t)blocks * kStreamTeams * f.scratch_slot));
         f.scratch = sc.deferred.as<uint8_t>();
-        stream_fused_kernel<<<blocks, kStreamThreads, fused_smem, stream>>>(f);
+        stream_fused_kernel<<<blocks, kStreamTeams * kStreamThreads, fused_smem, stream>>>(f);
         stream_fused_verify_kernel<<<(unsigned)std::min<uint64_t>((f.num_tiles + 255) / 256, 1024), 256, 0, stream>>>(f);
         ctx->launches += 2;
         HB_CUDA_TRY(cudaGetLastError());

@@ -35,6 +35,7 @@ names = ["prep (ticket, table, stage, sort)", "decode", "scan+publish", "rows->i
 tot = sum(buf[i] for i in range(8))
 print("scout: %.0f cycles per resolve, %.1f retries and %.1f rounds per resolve" % (buf[8] / max(1, buf[10]) * (buf[10] / max(1.0, reps * n / 224.0)), buf[9] / (reps * n / 224.0), buf[10] / (reps * n / 224.0)))
 print("scout resolve durations: <4K %d  <16K %d  <64K %d  <256K %d  more %d   max %d cycles" % (buf[11], buf[12], buf[13], buf[14], buf[15], buf[7]))
+print("fast loop: %.1f cycles per round of 6 steps (longest lane of each warp)" % (buf[14] / max(1, buf[15])))
 print("slow resolves by hand-off number: h=0 %d  h=1 %d  later %d" % (buf[5], buf[6], buf[13]))
 for i in range(6):
     print("phase %d %-55s %6.1f %%   %8.0f cycles/block/call" % (i, names[i], 100.0 * buf[i] / max(tot, 1), buf[i] / reps / 296.0))
