@@ -1614,34 +1614,10 @@ struct StreamFusedArgs {
     uint32_t lut2_count, lut2_trap;
     uint32_t num_tiles;
     uint32_t row_words;      // row stride in words (odd)
-    uint8_t *scratch;        // deferred output: one slot of scratch_slot bytes per block (16-byte aligned)
-    uint32_t scratch_slot;
 };
 
 __device__ __forceinline__ uint64_t fused_chunk_stop(const StreamArgs &a, uint64_t k) {
     return k + 1 == a.num_chunks ? a.end_bit : (k + 1) * kChunkBits;
-}
-
-// Whole block: the tile whose dense image sits in `slot` goes to its final place, `tile_base` being known now;
-// the tile of the stream's last chunk also carries the item-level results.
-__device__ __forceinline__ void stream_flush_tile(
-    uint32_t tid, const StreamFusedArgs &f, const uint8_t *slot, uint64_t tile_base, uint32_t total, bool last_tile, uint32_t last_rel,
-    uint64_t cbits, uint32_t my_term) {
-    const BatchView &b = f.b;
-    const StreamArgs &a = f.s;
-    if (last_tile && tid == 0) {
-        const uint64_t nsym = tile_base + last_rel;
-        b.out_offsets[0] = 0;
-        b.out_offsets[1] = nsym;
-        if (b.out_lens) b.out_lens[0] = nsym;
-        if (b.status) b.status[0] = my_term == kTermUnknown ? kStatusUnknownSymbol : kStatusOk;
-        if (b.consumed || b.leftover_working_bits || b.leftover_num_bits)
-            leftover_state(a.in_aligned + (a.begin_bit >> 3), (a.end_bit - a.begin_bit) >> 3, cbits,
-                           my_term == kTermUnknown, b.consumed, b.leftover_working_bits, b.leftover_num_bits);
-    }
-    const uint64_t room = tile_base < b.out_capacity ? b.out_capacity - tile_base : 0;
-    const uint32_t ncopy = (uint32_t)min((uint64_t)total, room);
-    block_copy_realign(slot, b.out + tile_base, ncopy, tid, kStreamThreads);
 }
 
 // Shared state of one team of stream_fused_kernel (the two teams of a block share one copy of the decode table,
@@ -1651,33 +1627,39 @@ struct StreamTeamShared {
     uint32_t nsym[kStreamThreads];
     uint8_t term[kStreamThreads];
     uint32_t warp_sum[kStreamThreads / 32];
-    uint64_t prefix, last_cbits;
+    uint64_t last_cbits;
     uint32_t tile, first_term, total, last_rel, last_term, flag;
+    uint32_t hand_tile[2];     // workers -> scout, by hand-off parity
+    uint64_t hand_prefix[2];   // scout -> workers
 };
 constexpr int kStreamTeams = 2;
-// team barriers: 1 + team (plain), and the OR-reduction of a predicate over the team
-__device__ __forceinline__ void stream_team_sync(uint32_t team) { asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "n"(kStreamThreads) : "memory"); }
+constexpr int kStreamTeamThreads = kStreamThreads + 32;  // 8 worker warps + 1 scout warp (see decode_batch_kernel)
+// team barriers, 5 per team: workers among themselves 5 t + 1 (plain, and the OR-reduction of a predicate over
+// the team); hand-off of a tile to the scout 5 t + 2 + parity; the scout's result 5 t + 4 + parity
+__device__ __forceinline__ void stream_team_sync(uint32_t team) { asm volatile("bar.sync %0, %1;" ::"r"(5 * team + 1), "n"(kStreamThreads) : "memory"); }
+__device__ __forceinline__ void stream_bar_arrive(uint32_t id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(kStreamTeamThreads) : "memory"); }
+__device__ __forceinline__ void stream_bar_sync(uint32_t id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kStreamTeamThreads) : "memory"); }
 __device__ __forceinline__ bool stream_team_or(uint32_t team, bool pred) {
     uint32_t out;
     asm volatile(
         "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 p, %1, 0;\n\tbarrier.red.or.pred q, %2, %3, p;\n\tselp.u32 %0, 1, 0, q;\n\t}"
         : "=r"(out)
-        : "r"((uint32_t)pred), "r"(1 + team), "n"(kStreamThreads)
+        : "r"((uint32_t)pred), "r"(5 * team + 1), "n"(kStreamThreads)
         : "memory");
     return out != 0;
 }
 
-__global__ void __launch_bounds__(kStreamTeams * kStreamThreads, 1) stream_fused_kernel(StreamFusedArgs f) {
+__global__ void __launch_bounds__(kStreamTeams * kStreamTeamThreads, 1) stream_fused_kernel(StreamFusedArgs f) {
     extern __shared__ __align__(128) uint32_t s_lut[];  // [LUT2][team 0: stage, rows][team 1: stage, rows]
     __shared__ StreamTeamShared s_teams[kStreamTeams];
     const StreamArgs &a = f.s;
-    const uint32_t team = threadIdx.x / kStreamThreads, tid = threadIdx.x - team * kStreamThreads;
+    const uint32_t team = threadIdx.x / kStreamTeamThreads, tid = threadIdx.x - team * kStreamTeamThreads;
     StreamTeamShared &sh = s_teams[team];
     uint16_t (&s_entry)[kStreamThreads] = sh.entry, (&s_exit)[kStreamThreads] = sh.exit;
     uint32_t (&s_nsym)[kStreamThreads] = sh.nsym;
     uint8_t (&s_term)[kStreamThreads] = sh.term;
     uint32_t (&s_warp_sum)[kStreamThreads / 32] = sh.warp_sum;
-    uint64_t &s_prefix = sh.prefix, &s_last_cbits = sh.last_cbits;
+    uint64_t &s_last_cbits = sh.last_cbits;
     uint32_t &s_tile = sh.tile, &s_first_term = sh.first_term, &s_total = sh.total, &s_last_rel = sh.last_rel,
              &s_last_term = sh.last_term;
     const uint32_t lut_pad = 2u * f.lut2_count;
@@ -1691,10 +1673,20 @@ __global__ void __launch_bounds__(kStreamTeams * kStreamThreads, 1) stream_fused
     const Lut2 lut2 = lut2_load(reinterpret_cast<uint2 *>(s_lut), f.lut2, f.lut2_count, a.root_bits, f.lut2_trap);
     __syncthreads();  // the LUT is in place
     const uint32_t k = tid, lane = lane_id(), warp = tid >> 5;
+    // ---- scout: the position of the tile's output (the symbols of all tiles before it), summed next to the
+    // tile's own work (see decode_batch_kernel) ---------------------------------------------------------------
+    if (warp == kStreamThreads / 32) {
+        for (uint32_t h = 0;; ++h) {
+            stream_bar_sync(5 * team + 2 + (h & 1));
+            const uint32_t t = sh.hand_tile[h & 1];
+            if (t == kDecDone) return;
+            const uint64_t prefix = lookback_exclusive(f.tile_state, t);
+            if (lane == 0) sh.hand_prefix[h & 1] = prefix;
+            stream_bar_arrive(5 * team + 4 + (h & 1));
+        }
+    }
+    uint32_t hand = 0;
     const uint32_t row_addr = (uint32_t)__cvta_generic_to_shared(s_rows) + k * row_bytes;
-    uint8_t *const slot = f.scratch + ((size_t)blockIdx.x * kStreamTeams + team) * f.scratch_slot;  // this block's deferred-output slot
-    bool pend = false;  // a tile's image sits in the slot (block-uniform)
-    uint32_t pend_tile = 0, pend_total = 0;
 
     while (true) {
         stream_team_sync(team);  // previous tile fully done (and the LUT is in place on the first trip)
@@ -1705,6 +1697,9 @@ __global__ void __launch_bounds__(kStreamTeams * kStreamThreads, 1) stream_fused
         stream_team_sync(team);
         const uint32_t tile = s_tile;
         if (tile >= f.num_tiles) break;
+        if (k == 0) sh.hand_tile[hand & 1] = tile;
+        stream_bar_arrive(5 * team + 2 + (hand & 1));  // the scout starts on the tile's position
+        ++hand;
         const uint64_t c0 = (uint64_t)tile * kStreamThreads;
         stream_stage(a, c0, s_in, tid);
         stream_team_sync(team);
@@ -1839,12 +1834,7 @@ __global__ void __launch_bounds__(kStreamTeams * kStreamThreads, 1) stream_fused
             s_last_term = s_term[k];
         }
 
-        // ---- DEFERRED OUTPUT (see decode_batch_kernel): this tile's dense image is parked in the block's scratch
-        // slot; the previous tile, whose prefix warp 0 resolves while the others build the image, goes out now.
-        if (warp == 0 && pend) {
-            const uint64_t prefix = lookback_resolve(f.tile_state, pend_tile, pend_total);
-            if (lane == 0) s_prefix = prefix;
-        }
+        // ---- rows -> dense image in shared memory -> its final place (the scout has the position by now) -----------
         {
             // rows that start before `front` lie where the dense image may grow: they go first (their destination
             // ends inside the stage area); the image (<= 256 rows) ends before row offset `front` + stage
@@ -1858,29 +1848,28 @@ __global__ void __launch_bounds__(kStreamTeams * kStreamThreads, 1) stream_fused
                 stream_team_sync(team);
             }
         }
-        if (pend) {
-            stream_flush_tile(tid, f, slot, s_prefix, pend_total, pend_tile == f.num_tiles - 1, s_last_rel, s_last_cbits, s_last_term);
-            stream_team_sync(team);  // the slot is free again
+        stream_bar_sync(5 * team + 4 + ((hand - 1) & 1));
+        const uint64_t tile_base = sh.hand_prefix[(hand - 1) & 1];
+        if (k == 0 && tile > 0)
+            st_relaxed_u64(&f.tile_state[tile], (kLbPrefix << kLbFlagShift) | ((tile_base + total) & kLbValueMask));
+        if (tile == f.num_tiles - 1 && k == 0) {
+            const BatchView &b = f.b;
+            const uint64_t nsym_all = tile_base + s_last_rel;
+            b.out_offsets[0] = 0;
+            b.out_offsets[1] = nsym_all;
+            if (b.out_lens) b.out_lens[0] = nsym_all;
+            if (b.status) b.status[0] = s_last_term == kTermUnknown ? kStatusUnknownSymbol : kStatusOk;
+            if (b.consumed || b.leftover_working_bits || b.leftover_num_bits)
+                leftover_state(a.in_aligned + (a.begin_bit >> 3), (a.end_bit - a.begin_bit) >> 3, s_last_cbits,
+                               s_last_term == kTermUnknown, b.consumed, b.leftover_working_bits, b.leftover_num_bits);
         }
         {
-            const uint32_t nvec = (total + 15u) >> 4;
-            const uint4 *sv = reinterpret_cast<const uint4 *>(s_dense);
-            uint4 *gv = reinterpret_cast<uint4 *>(slot);
-            for (uint32_t v = k; v < nvec; v += kStreamThreads) gv[v] = sv[v];
+            const uint64_t room = tile_base < f.b.out_capacity ? f.b.out_capacity - tile_base : 0;
+            smem_copy_out(s_dense, f.b.out + tile_base, (uint32_t)min((uint64_t)total, room), k, kStreamThreads);
         }
-        pend = true;
-        pend_tile = tile;
-        pend_total = total;
     }
-    // the last tile this block decoded is still in its slot
-    if (pend) {
-        if (warp == 0) {
-            const uint64_t prefix = lookback_resolve(f.tile_state, pend_tile, pend_total);
-            if (lane == 0) s_prefix = prefix;
-        }
-        stream_team_sync(team);
-        stream_flush_tile(tid, f, slot, s_prefix, pend_total, pend_tile == f.num_tiles - 1, s_last_rel, s_last_cbits, s_last_term);
-    }
+    if (k == 0) sh.hand_tile[hand & 1] = kDecDone;
+    stream_bar_arrive(5 * team + 2 + (hand & 1));
 }
 
 // Every tile's first chunk must have entered exactly where the previous tile's last chunk left.

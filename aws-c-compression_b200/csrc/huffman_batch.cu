@@ -552,10 +552,7 @@ int decode_stream_fast(
         a.gate = f.fail;
         HB_CUDA_TRY(cudaFuncSetAttribute(stream_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem));
         const unsigned blocks = (unsigned)std::min<uint64_t>((f.num_tiles + kStreamTeams - 1) / kStreamTeams, (uint64_t)ctx->sm_count);
-        f.scratch_slot = (uint32_t)((team_bytes + 64 + 255) & ~size_t(255));
-        HB_CUDA_TRY(sc.deferred.reserve((size_t)blocks * kStreamTeams * f.scratch_slot));
-        f.scratch = sc.deferred.as<uint8_t>();
-        stream_fused_kernel<<<blocks, kStreamTeams * kStreamThreads, fused_smem, stream>>>(f);
+        stream_fused_kernel<<<blocks, kStreamTeams * kStreamTeamThreads, fused_smem, stream>>>(f);
         stream_fused_verify_kernel<<<(unsigned)std::min<uint64_t>((f.num_tiles + 255) / 256, 1024), 256, 0, stream>>>(f);
         ctx->launches += 2;
         HB_CUDA_TRY(cudaGetLastError());
