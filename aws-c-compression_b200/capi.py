@@ -124,7 +124,8 @@ EXPORTED_SYMBOLS = [
     "aws_huffman_table_coder_init", "aws_huffman_table_coder_clean_up",
     "aws_hpack_string_encode_batch", "aws_hpack_string_decode_batch",
     "aws_hpack_string_encode_batch_device", "aws_hpack_string_decode_batch_device",
-    "aws_huffman_get_encoded_length_batch", "aws_huffman_batch_ctx_synchronize",
+    "aws_huffman_get_encoded_length_batch", "aws_huffman_get_encoded_length_batch_device",
+    "aws_huffman_encode_batch_multi", "aws_huffman_decode_batch_multi", "aws_huffman_batch_ctx_synchronize",
     "aws_huffman_batch_ctx_stream", "aws_huffman_batch_ctx_device", "aws_huffman_batch_ctx_launch_count",
     "aws_huffman_batch_plan_shards", "aws_huffman_batch_concat_offsets",
 ]
@@ -199,6 +200,12 @@ class Library:
             getattr(L, name).restype = C.c_int
         L.aws_huffman_get_encoded_length_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.aws_huffman_get_encoded_length_batch.restype = C.c_int
+        L.aws_huffman_get_encoded_length_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
+                                                                 C.c_void_p]
+        L.aws_huffman_get_encoded_length_batch_device.restype = C.c_int
+        for name in ("aws_huffman_encode_batch_multi", "aws_huffman_decode_batch_multi"):
+            getattr(L, name).argtypes = [C.c_void_p, C.c_size_t, P(aws_huffman_batch)]
+            getattr(L, name).restype = C.c_int
         L.aws_huffman_batch_ctx_synchronize.argtypes = [C.c_void_p]
         L.aws_huffman_batch_ctx_synchronize.restype = C.c_int
         L.aws_huffman_batch_ctx_stream.argtypes = [C.c_void_p]
@@ -527,6 +534,12 @@ class BatchContext:
             raise CodecError(self.library.last_error(), "aws_huffman_get_encoded_length_batch")
         return lens
 
+    def encoded_lengths_device(self, n, in_, in_offsets, lens, stream=None):
+        rc = self.library.lib.aws_huffman_get_encoded_length_batch_device(
+            self.handle, _ptr(in_), _ptr(in_offsets), n, _ptr(lens), stream or 0)
+        if rc != 0:
+            raise CodecError(self.library.last_error(), "aws_huffman_get_encoded_length_batch_device")
+
     # ---- device-buffer entry points (torch CUDA tensors; enqueued on `stream`) ----
     def encode_device(self, n, arrays, in_size, out_capacity, stream=None):
         self._call("aws_huffman_encode_batch_device", n, arrays, int(out_capacity), stream=stream or 0,
@@ -535,3 +548,29 @@ class BatchContext:
     def decode_device(self, n, arrays, in_size, out_capacity, stream=None):
         self._call("aws_huffman_decode_batch_device", n, arrays, int(out_capacity), stream=stream or 0,
                    in_size=int(in_size))
+
+
+def run_multi(contexts, encode, data, in_offsets, out_capacity):
+    """aws_huffman_encode_batch_multi / aws_huffman_decode_batch_multi: one packed batch over several contexts
+    (host buffers, numpy in / numpy out)."""
+    data = np.ascontiguousarray(data, dtype=np.uint8)
+    in_offsets = np.ascontiguousarray(in_offsets, dtype=np.uint64)
+    n = len(in_offsets) - 1
+    res = {"out": np.zeros(max(int(out_capacity), 1), dtype=np.uint8), "out_offsets": np.zeros(n + 1, dtype=np.uint64),
+           "out_lens": np.zeros(n, dtype=np.uint64), "status": np.zeros(n, dtype=np.int32),
+           "consumed": np.zeros(n, dtype=np.uint64)}
+    b = aws_huffman_batch()
+    b.n = n
+    b.in_size = int(in_offsets[n]) if n else 0
+    b.out_capacity = int(out_capacity)
+    b.in_ = _ptr(data)
+    b.in_offsets = _ptr(in_offsets)
+    for key, value in res.items():
+        setattr(b, key, _ptr(value))
+    lib = contexts[0].library
+    handles = (C.c_void_p * len(contexts))(*[c.handle for c in contexts])
+    fn = lib.lib.aws_huffman_encode_batch_multi if encode else lib.lib.aws_huffman_decode_batch_multi
+    rc = fn(handles, len(contexts), C.byref(b))
+    if rc != 0:
+        raise CodecError(lib.last_error(), "aws_huffman_%s_batch_multi" % ("encode" if encode else "decode"))
+    return res

@@ -21,6 +21,7 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -1616,6 +1617,107 @@ int aws_huffman_batch_concat_offsets(
     }
     global_offsets[at] = base;
     return AWS_OP_SUCCESS;
+}
+
+// One batch over several contexts (one per GPU of the box, or several on one GPU): plan by bytes, one host thread
+// per context drives its shard through that context's own (pipelined) host path into a private buffer, and the
+// host concatenates payloads and offsets. No collective: the shards never talk to each other.
+static int hb_run_multi(struct aws_huffman_batch_ctx *const *ctxs, size_t n_ctx, const struct aws_huffman_batch *b, bool encode) {
+    if (!ctxs || n_ctx == 0) return aws_raise_error(AWS_ERROR_INVALID_ARGUMENT);
+    for (size_t d = 0; d < n_ctx; ++d)
+        if (!ctxs[d]) return aws_raise_error(AWS_ERROR_INVALID_ARGUMENT);
+    if (check_batch(b)) return AWS_OP_ERR;
+    if (b->out_caps) return aws_raise_error(AWS_ERROR_INVALID_ARGUMENT);  // packed layout only
+    const size_t n = b->n;
+    if (n == 0) {
+        if (b->out_offsets) b->out_offsets[0] = 0;
+        return AWS_OP_SUCCESS;
+    }
+    if (n_ctx == 1) return encode ? aws_huffman_encode_batch(ctxs[0], b) : aws_huffman_decode_batch(ctxs[0], b);
+    std::vector<size_t> begin(n_ctx + 1);
+    if (aws_huffman_batch_plan_shards(b->in_offsets, n, n_ctx, begin.data())) return AWS_OP_ERR;
+    struct Shard {
+        std::vector<uint64_t> in_off, out_off;
+        std::vector<uint8_t> out;
+        int rc = AWS_OP_SUCCESS, err = 0;
+    };
+    std::vector<Shard> shards(n_ctx);
+    std::vector<std::thread> threads;
+    for (size_t d = 0; d < n_ctx; ++d) {
+        threads.emplace_back([&, d]() {
+            Shard &sh = shards[d];
+            const size_t a = begin[d], nd = begin[d + 1] - a;
+            if (nd == 0) return;
+            const uint64_t in0 = b->in_offsets[a], bytes_in = b->in_offsets[a + nd] - in0;
+            const uint32_t max_len = std::max<uint32_t>(1, ctxs[d]->tables.max_len), min_len = std::max<uint32_t>(1, ctxs[d]->tables.min_len);
+            const uint64_t room = (encode ? bytes_in * ((max_len + 7) / 8) : (bytes_in * 8) / min_len) + 64;
+            sh.in_off.resize(nd + 1);
+            for (size_t i = 0; i <= nd; ++i) sh.in_off[i] = b->in_offsets[a + i] - in0;
+            sh.out_off.assign(nd + 1, 0);
+            sh.out.resize(room);
+            aws_huffman_batch sb = *b;
+            sb.n = nd;
+            sb.in = b->in + in0;
+            sb.in_offsets = sh.in_off.data();
+            sb.in_size = bytes_in;
+            sb.out = sh.out.data();
+            sb.out_capacity = room;
+            sb.out_offsets = sh.out_off.data();
+            if (b->out_lens) sb.out_lens = b->out_lens + a;
+            if (b->status) sb.status = b->status + a;
+            if (b->consumed) sb.consumed = b->consumed + a;
+            if (b->overflow_pattern) sb.overflow_pattern = b->overflow_pattern + a;
+            if (b->overflow_num_bits) sb.overflow_num_bits = b->overflow_num_bits + a;
+            if (b->leftover_working_bits) sb.leftover_working_bits = b->leftover_working_bits + a;
+            if (b->leftover_num_bits) sb.leftover_num_bits = b->leftover_num_bits + a;
+            sh.rc = encode ? aws_huffman_encode_batch(ctxs[d], &sb) : aws_huffman_decode_batch(ctxs[d], &sb);
+            if (sh.rc != AWS_OP_SUCCESS) sh.err = aws_last_error();  // (the error slot is per thread)
+        });
+    }
+    for (std::thread &t : threads) t.join();
+    for (const Shard &sh : shards)
+        if (sh.rc != AWS_OP_SUCCESS) return aws_raise_error(sh.err ? sh.err : AWS_ERROR_COMPRESSION_DEVICE_FAILURE);
+    // the concatenation step
+    std::vector<const uint64_t *> ptrs(n_ctx);
+    std::vector<size_t> items(n_ctx);
+    for (size_t d = 0; d < n_ctx; ++d) {
+        items[d] = begin[d + 1] - begin[d];
+        static const uint64_t zero = 0;
+        ptrs[d] = items[d] ? shards[d].out_off.data() : &zero;
+    }
+    if (aws_huffman_batch_concat_offsets(ptrs.data(), items.data(), n_ctx, b->out_offsets)) return AWS_OP_ERR;
+    if (b->out_offsets[n] > b->out_capacity) return aws_raise_error(AWS_ERROR_SHORT_BUFFER);
+    for (size_t d = 0; d < n_ctx; ++d)
+        if (items[d]) memcpy(b->out + b->out_offsets[begin[d]], shards[d].out.data(), (size_t)shards[d].out_off[items[d]]);
+    return AWS_OP_SUCCESS;
+}
+
+int aws_huffman_encode_batch_multi(
+    struct aws_huffman_batch_ctx *const *ctxs, size_t n_ctx, const struct aws_huffman_batch *batch) {
+    return hb_run_multi(ctxs, n_ctx, batch, true);
+}
+
+int aws_huffman_decode_batch_multi(
+    struct aws_huffman_batch_ctx *const *ctxs, size_t n_ctx, const struct aws_huffman_batch *batch) {
+    return hb_run_multi(ctxs, n_ctx, batch, false);
+}
+
+int aws_huffman_get_encoded_length_batch_device(
+    struct aws_huffman_batch_ctx *ctx,
+    const uint8_t *in,
+    const uint64_t *in_offsets,
+    size_t n,
+    uint64_t *lens,
+    void *cuda_stream) {
+    if (!ctx || (n && (!in_offsets || !lens))) return aws_raise_error(AWS_ERROR_INVALID_ARGUMENT);
+    if (n == 0) return AWS_OP_SUCCESS;
+    cudaStream_t st;
+    if (device_call_begin(ctx, cuda_stream, &st)) return AWS_OP_ERR;
+    const unsigned blocks = (unsigned)((n + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    encoded_length_kernel<<<blocks, kWarpsPerBlock * 32, 0, st>>>(ctx->tables, in, in_offsets, n, lens);
+    ++ctx->launches;
+    HB_CUDA_TRY(cudaGetLastError());
+    return device_call_end(ctx, st, AWS_OP_SUCCESS);
 }
 
 }  // extern "C"

@@ -167,6 +167,17 @@ int aws_huffman_get_encoded_length_batch(
     size_t n,
     uint64_t *lens);
 
+/* The same with device pointers (reference huffman.c:107-129 per item); enqueued on `cuda_stream`
+ * (NULL = the context's own stream), returns without waiting. */
+AWS_COMPRESSION_API
+int aws_huffman_get_encoded_length_batch_device(
+    struct aws_huffman_batch_ctx *ctx,
+    const uint8_t *in,
+    const uint64_t *in_offsets,
+    size_t n,
+    uint64_t *lens,
+    void *cuda_stream);
+
 /* Blocks until everything enqueued on the context's own stream has finished. */
 AWS_COMPRESSION_API
 int aws_huffman_batch_ctx_synchronize(struct aws_huffman_batch_ctx *ctx);
@@ -198,6 +209,27 @@ int aws_huffman_batch_concat_offsets(
     const size_t *shard_items,
     size_t num_shards,
     uint64_t *global_offsets);
+
+/*
+ * One packed batch over several contexts — normally one per GPU of the box (BASELINE configs[4]); contexts on
+ * the same device are allowed. The batch is cut into n_ctx contiguous item ranges balanced by input bytes
+ * (aws_huffman_batch_plan_shards), every range runs through its context's host path on a host thread of its own,
+ * and payloads and offsets are concatenated on the host (aws_huffman_batch_concat_offsets). Per item the result is
+ * exactly that of aws_huffman_encode_batch / aws_huffman_decode_batch on one context: the reference's
+ * aws_huffman_encode / aws_huffman_decode (source/huffman.c:131-187, 213-286) per item. Host pointers, packed
+ * layout only (out_caps must be NULL). All contexts must have been created from the same coder.
+ */
+AWS_COMPRESSION_API
+int aws_huffman_encode_batch_multi(
+    struct aws_huffman_batch_ctx *const *ctxs,
+    size_t n_ctx,
+    const struct aws_huffman_batch *batch);
+
+AWS_COMPRESSION_API
+int aws_huffman_decode_batch_multi(
+    struct aws_huffman_batch_ctx *const *ctxs,
+    size_t n_ctx,
+    const struct aws_huffman_batch *batch);
 
 AWS_EXTERN_C_END
 AWS_POP_SANE_WARNING_LEVEL
