@@ -40,3 +40,32 @@ def test_reference_arm_prints_one_json_line():
     line = json.loads(out.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "GB/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_parity_gates_accept_the_oracle_and_reject_a_flipped_bit(oracle, oracle_tables):
+    """bench.py's parity gates (the reference on the same inputs) on outputs made by the oracle: equal as they
+    are, different after one flipped bit — in a string's bytes, in an offset, and in the middle of a stream whose
+    segments start at every bit phase."""
+    data, offs, _ = bench.cpu_sample("hpack_batch", 3000)
+    enc = oracle.encode_batch(oracle_tables["hpack"], 0xFF, data, offs, 4 * len(data))
+    total = int(enc["out_offsets"][-1])
+    out = enc["out"][:total].copy()
+    ok = bench.parity_batch(data, offs, out, enc["out_offsets"], 3)
+    assert ok["encoded_bytes_equal"] and ok["encoded_offsets_equal"] and ok["reference_decodes_gpu_bytes_to_input"]
+    assert ok["strings"] == 3000 and ok["encoded_bytes"] == total
+    bad = out.copy()
+    bad[total // 2] ^= 0x10
+    assert not bench.parity_batch(data, offs, bad, enc["out_offsets"], 3)["encoded_bytes_equal"]
+
+    stream, soff, _ = bench.cpu_sample("stream", 300_001)
+    senc = oracle.encode_batch(oracle_tables["hpack"], 0xFF, stream, soff, 4 * len(stream))
+    sbytes = int(senc["out_offsets"][-1])
+    sout = senc["out"][:sbytes + 8].copy()
+    good = bench.parity_stream(stream, sout, sbytes, 4, seg_bytes=7001, decode_prefix=5000)
+    assert good["encoded_bytes_equal"] and good["reference_decodes_gpu_prefix_to_input"] and good["segments"] == 43
+    for pos in (0, sbytes // 3, sbytes - 1):
+        for bit in (0x80, 0x01):
+            bad = sout.copy()
+            bad[pos] ^= bit
+            assert not bench.parity_stream(stream, bad, sbytes, 4, seg_bytes=7001, decode_prefix=5000)["encoded_bytes_equal"], (pos, bit)
+    assert not bench.parity_stream(stream, sout, sbytes + 1, 2, seg_bytes=7001, decode_prefix=5000)["encoded_bytes_equal"]
