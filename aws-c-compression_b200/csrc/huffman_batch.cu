@@ -16,6 +16,7 @@
 #include "encode_strings.cuh"
 #include "hpack_literals.cuh"
 #include "decode_fast.cuh"
+#include "decode_rows.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -77,11 +78,11 @@ struct GrowBuf {
 // Per-launch kernel scratch (tile descriptors, chunk records, ...). One per concurrent stream.
 struct Scratch {
     GrowBuf lens, tile_state, tile_first, chunks, chunk_lens, chunk_offsets, fused, slot_base, deferred, str_ctl, str_state,
-        str_tiles, str_bits, str_bits_first;
+        str_tiles, str_bits, str_bits_first, rows, row_pos, row_cnt, rows_ctl;
     void release() {
         GrowBuf *all[] = {&lens,          &tile_state, &tile_first,  &chunks,   &chunk_lens, &chunk_offsets,
                           &fused,         &slot_base,  &deferred,    &str_ctl,  &str_state,  &str_tiles,
-                          &str_bits,      &str_bits_first};
+                          &str_bits,      &str_bits_first, &rows,       &row_pos,     &row_cnt,  &rows_ctl};
         for (GrowBuf *g : all) g->release();
     }
 };
@@ -146,7 +147,8 @@ struct aws_huffman_batch_ctx {
     cudaStream_t scratch_stream = nullptr;
     bool scratch_busy = false;
     // switches, read once at context creation
-    bool force_generic = false, no_slots = false, no_strings = false, no_fused_stream = false;
+    bool force_generic = false, no_slots = false, no_strings = false, no_fused_stream = false, no_rows = false;
+    int rows_blocks_per_sm = 0, compact_blocks_per_sm = 0;
 };
 
 namespace {
@@ -496,6 +498,76 @@ int decode_batch_fast(
     return AWS_OP_SUCCESS;
 }
 
+// Packed layout, many strings: decode into worst-case spaced rows of a global scratch (decode_rows_kernel), then
+// counts -> offsets and rows -> dense output (compact_rows_kernel). decode_rows.cuh.
+constexpr size_t kCompactStageBytes = 56 * 1024, kCompactImageBytes = 42 * 1024;  // two blocks per SM
+int decode_batch_rows(
+    aws_huffman_batch_ctx *ctx, Scratch &sc, const hb::BatchView &v, uint64_t total_in, cudaStream_t stream) {
+    const uint32_t min_len = std::max<uint32_t>(1, ctx->tables.min_len);
+    const uint64_t rows_bytes = 16ull * (total_in / (2ull * min_len) + 1) + (uint64_t)kRowsSlack * v.n + 256;
+    const uint64_t num_pools = (v.n + kRowsPool - 1) / kRowsPool;
+    // strings per compaction tile: as many as fit the stage (rows at their worst-case spacing) with 15 % to spare, and
+    // the image if strings of average length decode to 85 % of their worst case (8 / min_len symbols per byte; the
+    // benchmark's data: 1.36 of 1.6); even. A tile that does not fit takes the slow route.
+    const double avg_row = std::max(1.0, (double)total_in * 8.0 / min_len / (double)v.n);
+    uint64_t per_tile = (uint64_t)std::min((double)kCompactStageBytes / (1.15 * (avg_row + kRowsSlack)),
+                                           (double)(kCompactImageBytes - 64) / (0.85 * 1.15 * avg_row));
+    per_tile = std::max<uint64_t>(2, std::min<uint64_t>(kCompactMaxItems, per_tile & ~uint64_t(1)));
+    const uint64_t num_tiles = (v.n + per_tile - 1) / per_tile;
+    if (num_pools >= 0xffffffffull || num_tiles >= 0xffffffffull) return aws_raise_error(AWS_ERROR_INVALID_ARGUMENT);
+    HB_CUDA_TRY(sc.rows.reserve(rows_bytes));
+    HB_CUDA_TRY(sc.row_pos.reserve(v.n * sizeof(uint64_t)));
+    HB_CUDA_TRY(sc.row_cnt.reserve((v.n + 2) * sizeof(uint32_t)));
+    // [look-back descriptors of the compaction: num_tiles][tickets: 2 words (+ pad)]
+    const size_t ctl_bytes = num_tiles * sizeof(uint64_t) + 64;
+    HB_CUDA_TRY(sc.rows_ctl.reserve(ctl_bytes));
+    HB_CUDA_TRY(cudaMemsetAsync(sc.rows_ctl.ptr, 0, ctl_bytes, stream));
+    uint32_t *tickets = reinterpret_cast<uint32_t *>(sc.rows_ctl.as<uint64_t>() + num_tiles);
+    DecRowsArgs a{};
+    a.b = v;
+    a.total_in = total_in;
+    a.lut2 = ctx->d_lut2;
+    a.lut2_count = ctx->lut2_count;
+    a.lut2_trap = ctx->lut2_trap;
+    a.root_bits = ctx->tables.lut_root_bits;
+    a.min_len = min_len;
+    a.rows = sc.rows.as<uint8_t>();
+    a.row_pos = sc.row_pos.as<uint64_t>();
+    a.cnt = sc.row_cnt.as<uint32_t>();
+    a.ticket = tickets;
+    a.num_pools = (uint32_t)num_pools;
+    const size_t rows_smem = (size_t)ctx->lut2_count * 8 + 1024 + (size_t)kRowsWarps * kRowsRingBytes;
+    if (!ctx->rows_blocks_per_sm) {
+        // (the attribute belongs to the kernel, not to the context, and tables differ in size: the limit is set to
+        // what the device allows once, the launches ask for what they need)
+        int per_sm = 0;
+        HB_CUDA_TRY(cudaFuncSetAttribute(decode_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+        HB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_rows_kernel, kRowsThreads, rows_smem));
+        ctx->rows_blocks_per_sm = std::max(1, per_sm);
+        HB_CUDA_TRY(cudaFuncSetAttribute(compact_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kCompactStageBytes + kCompactImageBytes)));
+        HB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, compact_rows_kernel, kCompactThreads, kCompactStageBytes + kCompactImageBytes));
+        ctx->compact_blocks_per_sm = std::max(1, per_sm);
+    }
+    const unsigned grid_r = (unsigned)std::min<uint64_t>(num_pools, (uint64_t)ctx->sm_count * ctx->rows_blocks_per_sm);
+    decode_rows_kernel<<<grid_r, kRowsThreads, rows_smem, stream>>>(a);
+    CompactArgs c{};
+    c.b = v;
+    c.rows = a.rows;
+    c.row_pos = a.row_pos;
+    c.cnt = a.cnt;
+    c.tile_state = sc.rows_ctl.as<uint64_t>();
+    c.ticket = tickets + 1;
+    c.num_tiles = (uint32_t)num_tiles;
+    c.items_per_tile = (uint32_t)per_tile;
+    c.stage_bytes = (uint32_t)kCompactStageBytes;
+    c.image_bytes = (uint32_t)kCompactImageBytes;
+    const unsigned grid_c = (unsigned)std::min<uint64_t>(num_tiles, (uint64_t)ctx->sm_count * ctx->compact_blocks_per_sm);
+    compact_rows_kernel<<<grid_c, kCompactThreads, kCompactStageBytes + kCompactImageBytes, stream>>>(c);
+    ctx->launches += 2;
+    HB_CUDA_TRY(cudaGetLastError());
+    return AWS_OP_SUCCESS;
+}
+
 // Packed layout, one long stream: chunked speculative decode. The fused single-pass kernel does the
 // work; the multi-kernel path behind it only runs (on the device's own decision, no host round trip)
 // when the fused kernel raised its `fail` flag: a stream that does not self-synchronise, or that stops
@@ -590,6 +662,7 @@ int decode_on_device(
     const bool force_generic = ctx->force_generic;
     if (!v.resume && !v.out_caps && ctx->tables.lut_count <= kDecLutMaxSmem && !force_generic) {
         if (v.n == 1 && total_in >= kStreamMinBytes) return decode_stream_fast(ctx, sc, v, total_in, stream);
+        if (!ctx->no_rows) return decode_batch_rows(ctx, sc, v, total_in, stream);
         return decode_batch_fast(ctx, sc, v, total_in, stream);
     }
     if (!v.out_lens) {
@@ -1285,6 +1358,7 @@ static int hb_ctx_from_codes(
     ctx->no_slots = getenv("AWS_HUFFMAN_BATCH_NO_SLOTS") != nullptr;
     ctx->no_strings = getenv("AWS_HUFFMAN_BATCH_NO_STRINGS") != nullptr;
     ctx->no_fused_stream = getenv("AWS_HUFFMAN_BATCH_NO_FUSED_STREAM") != nullptr;
+    ctx->no_rows = getenv("AWS_HUFFMAN_BATCH_ROWS") == nullptr;  // (the two-kernel decoder is opt-in: measured slower, decode_rows.cuh)
     HB_CTX_TRY(cudaMalloc(&ctx->d_enc, sizeof(enc)));
     HB_CTX_TRY(cudaMalloc(&ctx->d_lut, (size_t)lut.count * sizeof(uint32_t)));
     HB_CTX_TRY(cudaMemcpy(ctx->d_enc, enc, sizeof(enc), cudaMemcpyHostToDevice));
