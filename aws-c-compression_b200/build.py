@@ -103,8 +103,10 @@ def build(force=False, verbose=False):
             obj = os.path.join(OBJ, os.path.basename(src) + ".o")
             _run([NVCC] + NVCC_FLAGS + inc + ["-Xptxas", "-v", "-c", src, "-o", obj], verbose)
             objs.append(obj)
+        # (linked next to its final place and renamed: a snapshot of the tree never sees half a library)
         _run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xlinker", "-Bsymbolic",
-              "-o", PRODUCT_LIB] + objs, verbose)
+              "-o", PRODUCT_LIB + ".tmp"] + objs, verbose)
+        os.replace(PRODUCT_LIB + ".tmp", PRODUCT_LIB)
 
     # 3. coders emitted by our generator
     hpack_def = os.path.join(PKG, "tables", "hpack.def")

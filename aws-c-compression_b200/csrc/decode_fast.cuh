@@ -633,7 +633,11 @@ __device__ __forceinline__ Lut2Hit lut2_lookup(const Lut2 &t, uint32_t window) {
 }
 __device__ __forceinline__ uint32_t lut2_len1(uint32_t x) { return (x >> 16) & 63u; }
 
-template <bool kEmit, bool kPadded, bool kSkipHoles>
+// kInPlace: the row being written overlays the stream being read (decode_slots.cuh: the writer never passes the
+// reader, but what was read is gone): a lane that meets a hole cannot start over from here — it returns
+// kTermTrapped and the caller redoes the string from global memory — and nothing is stored beyond the last symbol.
+constexpr uint32_t kTermTrapped = 3;
+template <bool kEmit, bool kPadded, bool kSkipHoles, bool kInPlace = false>
 __device__ __forceinline__ SpanS decode_span_lean(
     const uint32_t *s_in, const Lut2 &t, uint32_t root_bits, uint32_t pos, uint32_t stop, uint32_t end, uint32_t out_addr) {
     constexpr uint32_t kParked = 0x80000000u;
@@ -652,6 +656,87 @@ __device__ __forceinline__ SpanS decode_span_lean(
 #ifdef HB_PHASE_TIMING
         const long long tl0 = clock64();
         uint32_t rounds = 0;
+#endif
+#ifndef HB_NO_BULK_ROUNDS
+        // Bulk rounds: a step consumes at most max(root_bits, 8) bits (a root entry, or one level of an 8-bit
+        // sub-table), so while a whole round is sure to start all its steps before pair_end no step needs the
+        // "still inside the span" predicate: two compares and a move less per step (33 -> 30 instructions; the decode
+        // step is bound by the ALU pipe, which takes one warp instruction every two cycles).
+        {
+            const uint32_t step_max = max(root_bits, 8u);
+            const uint32_t bulk_end = pair_end > kUnifiedSteps * step_max ? pair_end - kUnifiedSteps * step_max : 0u;
+            while (pos < bulk_end) {
+#ifdef HB_PHASE_TIMING
+                ++rounds;
+#endif
+#pragma unroll
+                for (int step = 0; step < kUnifiedSteps; ++step) {
+                    if (kEmit) {
+                        asm volatile(
+                            "{\n\t"
+                            ".reg .pred c, w;\n\t"
+                            ".reg .b32 win, idx, adr, x, u, t, sh, lo, sp, no, wadr;\n\t"
+                            "shf.l.wrap.b32 win, %2, %1, %0;\n\t"
+                            "shf.r.wrap.b32 idx, win, 0, %7;\n\t"
+                            "mad.lo.u32 adr, idx, 8, %8;\n\t"
+                            "ld.shared.v2.u32 {x, %7}, [adr];\n\t"
+                            "and.b32 %8, %7, 0x00ffffe0;\n\t"
+                            "shr.u32 u, %7, 24;\n\t"
+                            "add.u32 %0, %0, u;\n\t"
+                            "and.b32 t, x, 0xffff;\n\t"
+                            "shl.b32 sh, %6, 3;\n\t"
+                            "shf.l.wrap.b32 lo, 0, t, sh;\n\t"
+                            "shf.l.wrap.b32 sp, t, 0, sh;\n\t"
+                            "or.b32 lo, lo, %9;\n\t"
+                            "shr.u32 u, x, 30;\n\t"
+                            "add.u32 no, %6, u;\n\t"
+                            "xor.b32 u, no, %6;\n\t"
+                            "and.b32 u, u, 4;\n\t"
+                            "setp.ne.u32 w, u, 0;\n\t"
+                            "and.b32 wadr, %6, 0xfffffffc;\n\t"
+                            "@w st.shared.u32 [wadr], lo;\n\t"
+                            "selp.b32 %9, sp, lo, w;\n\t"
+                            "mov.b32 %6, no;\n\t"
+                            "setp.ge.s32 c, %0, %5;\n\t"
+                            "@c mov.b32 %1, %2;\n\t"
+                            "@c mov.b32 %2, %3;\n\t"
+                            "@c ld.shared.u32 %3, [%4];\n\t"
+                            "@c add.u32 %4, %4, 4;\n\t"
+                            "@c add.s32 %5, %5, 32;\n\t"
+                            "}"
+                            : "+r"(pos), "+r"(c.w0), "+r"(c.w1), "+r"(c.w2), "+r"(c.wa), "+r"(c.limit), "+r"(out_addr), "+r"(ns), "+r"(tb), "+r"(acc)
+                            :
+                            : "memory");
+                    } else {
+                        asm volatile(
+                            "{\n\t"
+                            ".reg .pred c;\n\t"
+                            ".reg .b32 win, idx, adr, x, u;\n\t"
+                            "shf.l.wrap.b32 win, %2, %1, %0;\n\t"
+                            "shf.r.wrap.b32 idx, win, 0, %6;\n\t"
+                            "mad.lo.u32 adr, idx, 8, %7;\n\t"
+                            "ld.shared.v2.u32 {x, %6}, [adr];\n\t"
+                            "and.b32 %7, %6, 0x00ffffe0;\n\t"
+                            "shr.u32 u, %6, 24;\n\t"
+                            "add.u32 %0, %0, u;\n\t"
+                            "setp.ge.s32 c, %0, %5;\n\t"
+                            "@c mov.b32 %1, %2;\n\t"
+                            "@c mov.b32 %2, %3;\n\t"
+                            "@c ld.shared.u32 %3, [%4];\n\t"
+                            "@c add.u32 %4, %4, 4;\n\t"
+                            "@c add.s32 %5, %5, 32;\n\t"
+                            "}"
+                            : "+r"(pos), "+r"(c.w0), "+r"(c.w1), "+r"(c.w2), "+r"(c.wa), "+r"(c.limit), "+r"(ns), "+r"(tb)
+                            :
+                            : "memory");
+                    }
+                }
+                if (tb == t.trap_tb) {  // no code matches: leave the loops, the exact loop below redoes the span
+                    pos |= kParked;
+                    tb = root_tb;
+                }
+            }
+        }
 #endif
         while (pos < pair_end || tb != root_tb) {
 #ifdef HB_PHASE_TIMING
@@ -742,12 +827,21 @@ __device__ __forceinline__ SpanS decode_span_lean(
         }
 #endif
         if (pos & kParked) {
+            if (kInPlace) {
+                r.term = kTermTrapped;
+                r.pos = pos0;
+                r.nsym = 0;
+                return r;
+            }
             pos = pos0;
             out_addr = out0;
             c.init<kPadded>(in_addr, pos);
         } else if (kEmit && (out_addr & 3u)) {
-            // the symbols still in `acc` (the bytes above them are spare: rows have slack)
-            asm volatile("st.shared.u32 [%0], %1;" ::"r"(out_addr & ~3u), "r"(acc) : "memory");
+            if (kInPlace) {  // the symbols still in `acc`, and not a byte more
+                for (uint32_t k = 0; k < (out_addr & 3u); ++k) sts_u8((out_addr & ~3u) + k, acc >> (8 * k));
+            } else {         // (the bytes above them are spare: rows have slack)
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(out_addr & ~3u), "r"(acc) : "memory");
+            }
         }
         // the rest of the span (or all of it, after a trap): one lookup at a time with the end-of-stream rules (the
         // window is the stream zero-extended, huffman.c:196-211; a code that does not fit ends the stream,

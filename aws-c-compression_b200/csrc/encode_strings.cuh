@@ -43,6 +43,9 @@ namespace hb {
 #ifndef HB_STR_TAB_COPIES
 #define HB_STR_TAB_COPIES 16
 #endif
+#ifndef HB_STR_PREFETCH2
+#define HB_STR_PREFETCH2 0
+#endif
 #ifndef HB_STR_PACK_BLOCKS
 #define HB_STR_PACK_BLOCKS 2
 #endif
@@ -123,6 +126,21 @@ __device__ __forceinline__ void str_walk(const uint8_t *p, uint32_t len, const u
             if (a + b < in_end) w[b >> 2] |= (uint32_t)a[b] << (8 * (b & 3));
         return make_uint4(w[0], w[1], w[2], w[3]);
     };
+#if HB_STR_PREFETCH2
+    // two vectors in flight ahead of the one being packed (the packing loop's top stall was the wait for its loads)
+    uint4 cur = load(0);
+    uint4 n1 = cur, n2 = cur;
+    if (nvec > 1) n1 = load(1);
+    if (nvec > 2) n2 = load(2);
+    f.masked(cur, r, min(16u, span));
+    for (uint32_t j = 1; j + 1 < nvec; ++j) {
+        cur = n1;
+        n1 = n2;
+        if (j + 2 < nvec) n2 = load(j + 2);
+        f.full(cur);
+    }
+    if (nvec > 1) f.masked(n1, 0u, span - 16u * (nvec - 1));
+#else
     uint4 cur = load(0);
     uint4 nxt = cur;
     if (nvec > 1) nxt = load(1);
@@ -133,6 +151,7 @@ __device__ __forceinline__ void str_walk(const uint8_t *p, uint32_t len, const u
         f.full(cur);
     }
     if (nvec > 1) f.masked(nxt, 0u, span - 16u * (nvec - 1));
+#endif
 }
 
 __device__ __forceinline__ uint32_t str_word(const uint4 &v, int k) {
@@ -147,7 +166,10 @@ __device__ __forceinline__ uint32_t str_word(const uint4 &v, int k) {
 // exclusive prefix over its vectors. The bits of a string are then cum(end) - cum(start), two look-ups; a
 // string that crosses tiles collects its pieces with atomicAdd. (First version: one thread per string with
 // the sorted walk of the pack kernel: 89 us for 1M strings; this one: see profiles/README.md.)
-constexpr int kBitsThreads = 256;
+#ifndef HB_BITS_THREADS
+#define HB_BITS_THREADS 256
+#endif
+constexpr int kBitsThreads = HB_BITS_THREADS;
 constexpr int kBitsVecsPerThread = 4;
 constexpr int kBitsTileVecs = kBitsThreads * kBitsVecsPerThread;  // 1024
 constexpr uint32_t kBitsTileBytes = 16u * kBitsTileVecs;          // 16 KiB of input per tile
@@ -192,14 +214,13 @@ struct StrBitsArgs {
     uint32_t num_bits_tiles;
 };
 
-__global__ void __launch_bounds__(kBitsThreads, 4) str_bits_kernel(const uint2 *__restrict__ enc_table, StrBitsArgs a) {
+__global__ void __launch_bounds__(kBitsThreads, 1024 / kBitsThreads) str_bits_kernel(const uint2 *__restrict__ enc_table, StrBitsArgs a) {
     __shared__ __align__(16) uint8_t s_lentab[256];
     __shared__ __align__(16) uint32_t s_pre[kBitsTileVecs][8];  // per vector: inclusive prefix after byte 2j | after byte 2j+1 << 16
     __shared__ uint32_t s_vex[kBitsTileVecs + 1];               // exclusive prefix over the vectors; [nvec] = the tile's total
     __shared__ uint32_t s_wsum[kBitsThreads / 32];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    s_lentab[tid] = (uint8_t)enc_table[tid].y;
-    const uint32_t tab = smem_addr(s_lentab);
+    for (uint32_t i = tid; i < 256; i += kBitsThreads) s_lentab[i] = (uint8_t)enc_table[i].y;
 
     // bits of the tile's bytes [0, x)
     auto cum = [&](uint32_t x) -> uint32_t {
@@ -212,13 +233,13 @@ __global__ void __launch_bounds__(kBitsThreads, 4) str_bits_kernel(const uint2 *
         return c;
     };
 
-    for (uint32_t tile = blockIdx.x; tile < a.num_bits_tiles; tile += gridDim.x) {
+    // the tile's vectors of this thread (zeros past the input's end)
+    uint4 v[kBitsVecsPerThread];
+    auto fetch = [&](uint32_t tile) {
         const uint64_t t0 = (uint64_t)tile * kBitsTileBytes;
         const uint32_t tile_len = (uint32_t)min((uint64_t)kBitsTileBytes, a.total_in - t0);
         const uint32_t nvec = (tile_len + 15u) >> 4;
         const uint4 *vp = reinterpret_cast<const uint4 *>(a.in + t0);
-        __syncthreads();  // the previous tile's look-ups are over (first trip: the table is in place)
-        uint4 v[kBitsVecsPerThread];
 #pragma unroll
         for (int i = 0; i < kBitsVecsPerThread; ++i) {
             const uint32_t vi = i * kBitsThreads + tid;
@@ -231,6 +252,12 @@ __global__ void __launch_bounds__(kBitsThreads, 4) str_bits_kernel(const uint2 *
                 v[i] = make_uint4(w[0], w[1], w[2], w[3]);
             }
         }
+    };
+    if (blockIdx.x < a.num_bits_tiles) fetch(blockIdx.x);
+    for (uint32_t tile = blockIdx.x; tile < a.num_bits_tiles; tile += gridDim.x) {
+        const uint64_t t0 = (uint64_t)tile * kBitsTileBytes;
+        const uint32_t tile_len = (uint32_t)min((uint64_t)kBitsTileBytes, a.total_in - t0);
+        __syncthreads();  // the previous tile's look-ups are over (first trip: the table is in place)
 #pragma unroll
         for (int i = 0; i < kBitsVecsPerThread; ++i) {
             const uint32_t vi = i * kBitsThreads + tid;
@@ -238,9 +265,8 @@ __global__ void __launch_bounds__(kBitsThreads, 4) str_bits_kernel(const uint2 *
 #pragma unroll
             for (int k = 0; k < 16; k += 2) {
                 const uint32_t w = str_word(v[i], k);
-                uint32_t l0, l1;
-                asm volatile("ld.shared.u8 %0, [%1];" : "=r"(l0) : "r"(tab + __byte_perm(w, 0, 0x4440 | (k & 3))));
-                asm volatile("ld.shared.u8 %0, [%1];" : "=r"(l1) : "r"(tab + __byte_perm(w, 0, 0x4440 | ((k + 1) & 3))));
+                const uint32_t l0 = s_lentab[__byte_perm(w, 0, 0x4440 | (k & 3))];
+                const uint32_t l1 = s_lentab[__byte_perm(w, 0, 0x4440 | ((k + 1) & 3))];
                 const uint32_t p0 = run + l0;
                 run = p0 + l1;
                 pk[k >> 1] = p0 | (run << 16);
@@ -249,6 +275,9 @@ __global__ void __launch_bounds__(kBitsThreads, 4) str_bits_kernel(const uint2 *
             *reinterpret_cast<uint4 *>(&s_pre[vi][4]) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
             s_vex[vi] = run;  // (raw totals first; scanned below)
         }
+        // the next tile's vectors are requested now (the registers are free again): their latency passes behind
+        // the scan and the strings' look-ups instead of in front of the next tile's work
+        if (tile + gridDim.x < a.num_bits_tiles) fetch(tile + gridDim.x);
         __syncthreads();
         // exclusive scan over the vectors in order: four consecutive vectors per thread
         uint32_t q[4], sum = 0;

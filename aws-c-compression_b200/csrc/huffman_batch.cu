@@ -17,6 +17,7 @@
 #include "hpack_literals.cuh"
 #include "decode_fast.cuh"
 #include "decode_rows.cuh"
+#include "decode_slots.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -149,6 +150,8 @@ struct aws_huffman_batch_ctx {
     // switches, read once at context creation
     bool force_generic = false, no_slots = false, no_strings = false, no_fused_stream = false, no_rows = false;
     int rows_blocks_per_sm = 0, compact_blocks_per_sm = 0;
+    bool no_slots_decode = false;
+    size_t slots_static_smem = 0;
 };
 
 namespace {
@@ -498,6 +501,51 @@ int decode_batch_fast(
     return AWS_OP_SUCCESS;
 }
 
+// Packed layout, many strings: decode_slots_kernel (decode_slots.cuh) — decode_batch_kernel with stage and rows in
+// one place, larger tiles for the same shared memory, rows straight to global memory.
+int decode_batch_slots(
+    aws_huffman_batch_ctx *ctx, Scratch &sc, const hb::BatchView &v, uint64_t total_in, cudaStream_t stream) {
+    if (!ctx->slots_static_smem) {
+        cudaFuncAttributes attr{};
+        HB_CUDA_TRY(cudaFuncGetAttributes(&attr, decode_slots_kernel));
+        ctx->slots_static_smem = attr.sharedSizeBytes;
+        // (the limit belongs to the kernel, not to the context: set to what the device allows, launches ask for less)
+        HB_CUDA_TRY(cudaFuncSetAttribute(
+            decode_slots_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024 - 1024 - attr.sharedSizeBytes)));
+    }
+    DecSlotsArgs a{};
+    a.b = v;
+    a.lut2 = ctx->d_lut2;
+    a.lut2_count = ctx->lut2_count;
+    a.lut2_trap = ctx->lut2_trap;
+    a.root_bits = ctx->tables.lut_root_bits;
+    a.min_len = std::min<uint32_t>(8, std::max<uint32_t>(1, ctx->tables.min_len));
+    const size_t lut_bytes = (size_t)a.lut2_count * 8;
+    const size_t avail = (size_t)227 * 1024 - 1024 - ctx->slots_static_smem - lut_bytes;
+    const size_t region = (avail / kDecTeams) & ~size_t(15);
+    a.region_bytes = (uint32_t)region;
+    // strings per tile: as many slots as fit the region at the batch's average length with 15 % to spare, in whole
+    // warps (a tile that does not fit takes the two-pass global route and every tile behind it waits for its count)
+    {
+        const double avg = std::max(1.0, (double)total_in / (double)v.n);
+        const uint64_t fit = (uint64_t)std::max(32.0, (double)region / (1.15 * (avg * 8.0 / a.min_len + kSlotSlack)));
+        a.items_per_tile = (uint32_t)std::min<uint64_t>(kSlotItemsPerTile, fit & ~uint64_t(31));
+    }
+    const uint64_t num_tiles = (v.n + a.items_per_tile - 1) / a.items_per_tile;
+    const size_t state_bytes = num_tiles * sizeof(uint64_t) + 256;
+    HB_CUDA_TRY(sc.tile_state.reserve(state_bytes));
+    HB_CUDA_TRY(cudaMemsetAsync(sc.tile_state.ptr, 0, state_bytes, stream));
+    a.tile_state = sc.tile_state.as<uint64_t>();
+    a.ticket = reinterpret_cast<uint32_t *>(a.tile_state + num_tiles);
+    a.num_tiles = (uint32_t)num_tiles;
+    const size_t smem = lut_bytes + kDecTeams * region;
+    const unsigned blocks = (unsigned)std::min<uint64_t>((num_tiles + kDecTeams - 1) / kDecTeams, (uint64_t)ctx->sm_count);
+    decode_slots_kernel<<<blocks, kDecTeams * kDecBlock, smem, stream>>>(a);
+    ++ctx->launches;
+    HB_CUDA_TRY(cudaGetLastError());
+    return AWS_OP_SUCCESS;
+}
+
 // Packed layout, many strings: decode into worst-case spaced rows of a global scratch (decode_rows_kernel), then
 // counts -> offsets and rows -> dense output (compact_rows_kernel). decode_rows.cuh.
 constexpr size_t kCompactStageBytes = 56 * 1024, kCompactImageBytes = 42 * 1024;  // two blocks per SM
@@ -654,6 +702,7 @@ int decode_stream_fast(
     return AWS_OP_SUCCESS;
 }
 
+inline bool num_tiles_ok(uint64_t n) { return n / 32 < 0xfffffff0ull; }
 constexpr uint64_t kStreamMinBytes = 64 * 1024;  // shorter single items go through the batch kernel
 
 int decode_on_device(
@@ -663,6 +712,7 @@ int decode_on_device(
     if (!v.resume && !v.out_caps && ctx->tables.lut_count <= kDecLutMaxSmem && !force_generic) {
         if (v.n == 1 && total_in >= kStreamMinBytes) return decode_stream_fast(ctx, sc, v, total_in, stream);
         if (!ctx->no_rows) return decode_batch_rows(ctx, sc, v, total_in, stream);
+        if (!ctx->no_slots_decode && num_tiles_ok(v.n)) return decode_batch_slots(ctx, sc, v, total_in, stream);
         return decode_batch_fast(ctx, sc, v, total_in, stream);
     }
     if (!v.out_lens) {
@@ -1065,7 +1115,9 @@ int hpack_decode_on_device(
     aws_huffman_batch_ctx *ctx, uint64_t n, const uint8_t *in, const uint64_t *in_off, uint64_t total_in, uint8_t *out,
     uint64_t out_capacity, uint64_t *out_off, int32_t *status, cudaStream_t st) {
     if (n == 0) return AWS_OP_SUCCESS;
-    if (n > 1 && ctx->tables.lut_count <= kDecLutMaxSmem && !getenv("AWS_HUFFMAN_BATCH_FORCE_GENERIC") &&
+    // (the one-kernel route copies raw literals into rows sized 8 len / min_len: a table whose shortest code is longer
+    // than a byte — not HPACK's — takes the multi-pass route)
+    if (n > 1 && ctx->tables.lut_count <= kDecLutMaxSmem && ctx->tables.min_len <= 8 && !getenv("AWS_HUFFMAN_BATCH_FORCE_GENERIC") &&
         !getenv("AWS_HUFFMAN_HPACK_PASSES")) {
         // one kernel: the batch decoder parses the literals in its string table, copies raw payloads, applies
         // the padding rule to what it leaves over and writes strings, offsets and status itself
@@ -1358,6 +1410,7 @@ static int hb_ctx_from_codes(
     ctx->no_slots = getenv("AWS_HUFFMAN_BATCH_NO_SLOTS") != nullptr;
     ctx->no_strings = getenv("AWS_HUFFMAN_BATCH_NO_STRINGS") != nullptr;
     ctx->no_fused_stream = getenv("AWS_HUFFMAN_BATCH_NO_FUSED_STREAM") != nullptr;
+    ctx->no_slots_decode = getenv("AWS_HUFFMAN_BATCH_SLOTS_DECODE") == nullptr;  // (opt-in: measured slower, decode_slots.cuh)
     ctx->no_rows = getenv("AWS_HUFFMAN_BATCH_ROWS") == nullptr;  // (the two-kernel decoder is opt-in: measured slower, decode_rows.cuh)
     HB_CTX_TRY(cudaMalloc(&ctx->d_enc, sizeof(enc)));
     HB_CTX_TRY(cudaMalloc(&ctx->d_lut, (size_t)lut.count * sizeof(uint32_t)));

@@ -342,6 +342,43 @@ def parity_stream(h_raw, h_enc, enc_bytes, threads, seg_bytes=8 << 20, decode_pr
             "host_threads": threads, "seconds": round(time.perf_counter() - t0, 2)}
 
 
+def host_codec_leg(total_bytes=64 << 20, piece=256 << 10):
+    """The reference-compatible STREAMING API on the host (what a one-string-per-call caller links): this
+    repository's host/huffman.c + its table-driven generated coder against the unmodified reference + the
+    reference generator's goto-tree coder, one core each, same bytes, through the helper both libraries export
+    with the same signature (huffman_test_transitive: encode, decode, compare; reference
+    source/huffman_testing.c:15-80). Pieces of 256 KiB: the reference keeps its scratch on the stack."""
+    import ctypes as C
+    import refcodec
+    import __graft_entry__ as graft
+    pkg = graft.load_package()
+    sampler = refcodec.zipf_symbol_sampler(refcodec.table_arrays("hpack")[1])
+    data = symbols_np(SEED_STREAM, 0, total_bytes, sampler)
+    pieces = [data[a:a + piece].tobytes() for a in range(0, total_bytes, piece)]
+    out = {"bytes": total_bytes, "piece_bytes": piece, "cores": 1,
+           "what": "huffman_test_transitive (encode + decode + compare) over the first %d B of the stream workload" % total_bytes}
+    ours = pkg.product_library().lib
+    legs = [("b200_host_library", ours, pkg.coders_library().coder("hpack"))]
+    if refcodec.RefLib.available():
+        ref = refcodec.RefLib()
+        ref.lib.huffman_test_transitive.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_size_t, C.POINTER(C.c_char_p)]
+        ref.lib.huffman_test_transitive.restype = C.c_int
+        legs.append(("reference", ref.lib, ref.coder("hpack")))
+    for name, lib, coder in legs:
+        msg = C.c_char_p()
+        lib.huffman_test_transitive(coder, pieces[0], len(pieces[0]), 0, C.byref(msg))  # warm
+        t0 = time.perf_counter()
+        for p in pieces:
+            if lib.huffman_test_transitive(coder, p, len(p), 0, C.byref(msg)) != 0:
+                raise RuntimeError("%s round trip failed: %s" % (name, msg.value))
+        dt = time.perf_counter() - t0
+        out[name + "_raw_gbs"] = total_bytes / dt / 1e9
+    if "reference_raw_gbs" in out:
+        out["speedup"] = out["b200_host_library_raw_gbs"] / out["reference_raw_gbs"]
+    return out
+
+
+
 # ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
@@ -855,6 +892,7 @@ def main():
             line["cpu_baseline"] = {"value": gbs, "unit": "GB/s", "cores": 1, "kind": kind,
                                     "sample": what + ", encode + decode, best of %d passes of %.1f s" % (repeats, dt),
                                     "host_cpus": os.cpu_count()}
+            line["host_codec"] = host_codec_leg()
         print(json.dumps(line))
     arm.ctx.close()
     if world > 1:

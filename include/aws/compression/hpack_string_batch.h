@@ -48,8 +48,11 @@ int aws_hpack_string_encode_batch(
  *     AWS_ERROR_SHORT_BUFFER                 the literal is cut short: no length byte, an unfinished length, or
  *                                            fewer payload octets than the length announces
  *     AWS_ERROR_INVALID_ARGUMENT             octets left over after the payload, or a length beyond 2^62
- *     AWS_ERROR_COMPRESSION_UNKNOWN_SYMBOL   the Huffman payload holds a bit sequence that is no code
- *     AWS_ERROR_COMPRESSION_INVALID_PADDING  padding of 8 bits or more, padding that is not all ones, EOS inside
+ *     AWS_ERROR_COMPRESSION_UNKNOWN_SYMBOL   the Huffman payload holds a bit sequence that is no code (this is also how an
+ *                                            EOS code with 32 bits or more of payload behind it reports: the decoder
+ *                                            stops there, exactly like aws_huffman_decode)
+ *     AWS_ERROR_COMPRESSION_INVALID_PADDING  padding of 8 bits or more, padding that is not all ones (an EOS code in the
+ *                                            last 32 bits of the payload reports here: it is a run of ones too long)
  * Items with a non-zero status decode to nothing (their output range is empty).
  */
 AWS_COMPRESSION_API

@@ -198,3 +198,36 @@ def test_rows_decoder_matches_the_oracle(pkg, coders, oracle, oracle_tables, mon
                 assert np.array_equal(got["out"][:produced], want["out"][:produced]), (table, shape)
         finally:
             ctx.close()
+
+
+def test_slots_decoder_matches_the_oracle(pkg, coders, oracle, oracle_tables, monkeypatch):
+    """The opt-in in-place decoder (decode_slots.cuh: stage and rows share one slot per string; recorded A/B partner of
+    decode_batch_kernel) against the oracle, same shapes as the rows decoder's test plus a batch whose first and
+    last strings touch the ends of the input buffer at every 16-byte phase."""
+    monkeypatch.setenv("AWS_HUFFMAN_BATCH_SLOTS_DECODE", "1")
+    rng = np.random.default_rng(777)
+    for table in ("hpack", "test"):
+        ctx = pkg.BatchContext(coders.coder(table), eos_padding=0xFF, device=0)
+        try:
+            for shape in range(5):
+                n = int(rng.integers(1, 5000))
+                lens = [rng.integers(0, 300, size=n), rng.integers(0, 12, size=n), rng.integers(200, 3000, size=n),
+                        np.where(rng.random(n) < 0.3, 0, rng.integers(1, 600, size=n)), rng.integers(1, 40, size=n)][shape]
+                offs = np.zeros(n + 1, dtype=np.uint64)
+                offs[1:] = np.cumsum(lens)
+                sampler = refcodec.zipf_symbol_sampler(refcodec.table_arrays(table)[1])
+                data = sampler[rng.integers(0, 65536, size=int(offs[-1]))]
+                enc = oracle.encode_batch(oracle_tables[table], 0xFF, data, offs, 4 * len(data) + 64)
+                total = int(enc["out_offsets"][-1])
+                payload = enc["out"][:total].copy()
+                if shape % 2 and total:
+                    hits = rng.integers(0, total, size=max(1, total // 400))
+                    payload[hits] ^= rng.integers(1, 256, size=len(hits)).astype(np.uint8)
+                want = oracle.decode_batch(oracle_tables[table], payload, enc["out_offsets"], 8 * total + 64)
+                got = ctx.decode(payload, enc["out_offsets"], 8 * total + 64)
+                for k in ("out_offsets", "out_lens", "status", "consumed", "leftover_working_bits", "leftover_num_bits"):
+                    assert np.array_equal(got[k], want[k]), (table, shape, k)
+                produced = int(want["out_offsets"][-1])
+                assert np.array_equal(got["out"][:produced], want["out"][:produced]), (table, shape)
+        finally:
+            ctx.close()
