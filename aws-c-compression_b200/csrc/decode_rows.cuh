@@ -27,7 +27,7 @@
 // The decode step is the lean 64-bit-entry step of decode_fast.cuh (one lookup per step whatever the table, two
 // symbols per root entry); the last < 32 bits of a string run the exact one-symbol loop with the reference's
 // end-of-stream rules (huffman.c:196-211, 240-255) on a 64-bit register. Results are bit-identical to
-// decode_batch_kernel (tests/test_gpu_multi.py::test_rows_decoder_matches_the_oracle).
+// decode_batch_kernel (tests/test_gpu_multi.py: the rows decoder test).
 #pragma once
 
 #include "decode_fast.cuh"
