@@ -425,16 +425,23 @@ __device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) {
 // fetched one word ahead, so the dependent chain of a step is funnel -> LUT load -> add and the stream
 // loads are off it. A span never leaves its padded row in here (the callers' spans end at a row boundary,
 // or fewer than 32 bits after one), so the words are consecutive in shared memory.
-struct StreamCursor {
+// kRaw: the stage holds the stream's bytes as they are in memory (a bulk copy put them there: decode_batch_kernel with
+// HB_DEC_TMA_STAGE); a word is byte-swapped when it is fetched.
+template <bool kRaw>
+struct StreamCursorT {
     uint32_t w0, w1, w2;
     uint32_t wa;  // shared-window address of the word after w2
     int limit;    // first bit position after w0
+    __device__ __forceinline__ static uint32_t fetch(uint32_t addr) {
+        const uint32_t v = lds_u32(addr);
+        return kRaw ? __byte_perm(v, 0, 0x0123) : v;
+    }
     template <bool kPadded>
     __device__ __forceinline__ void init(uint32_t in_addr, uint32_t pos) {
         wa = in_addr + (kPadded ? (pos >> 5) + (pos >> 10) : (pos >> 5)) * 4;
-        w0 = lds_u32(wa);
-        w1 = lds_u32(wa + 4);
-        w2 = lds_u32(wa + 8);
+        w0 = fetch(wa);
+        w1 = fetch(wa + 4);
+        w2 = fetch(wa + 8);
         wa += 12;
         limit = (int)((pos | 31u) + 1u);
     }
@@ -444,12 +451,13 @@ struct StreamCursor {
         if ((int)pos >= limit) {
             w0 = w1;
             w1 = w2;
-            w2 = lds_u32(wa);
+            w2 = fetch(wa);
             wa += 4;
             limit += 32;
         }
     }
 };
+using StreamCursor = StreamCursorT<false>;
 
 // Decodes stage bits from `pos` until `stop`; the stream itself ends at `end` (stop <= end; stage-relative
 // bit positions). Same rules and results as decode_smem (which follows the reference loop); symbols go
@@ -637,7 +645,7 @@ __device__ __forceinline__ uint32_t lut2_len1(uint32_t x) { return (x >> 16) & 6
 // reader, but what was read is gone): a lane that meets a hole cannot start over from here — it returns
 // kTermTrapped and the caller redoes the string from global memory — and nothing is stored beyond the last symbol.
 constexpr uint32_t kTermTrapped = 3;
-template <bool kEmit, bool kPadded, bool kSkipHoles, bool kInPlace = false>
+template <bool kEmit, bool kPadded, bool kSkipHoles, bool kInPlace = false, bool kRaw = false>
 __device__ __forceinline__ SpanS decode_span_lean(
     const uint32_t *s_in, const Lut2 &t, uint32_t root_bits, uint32_t pos, uint32_t stop, uint32_t end, uint32_t out_addr) {
     constexpr uint32_t kParked = 0x80000000u;
@@ -648,8 +656,8 @@ __device__ __forceinline__ SpanS decode_span_lean(
         const uint32_t fast_end = (end >= 32u) ? min(stop, end - 31u) : 0u;
         const uint32_t pair_end = fast_end > root_bits ? fast_end - root_bits : 0u;
         const uint32_t in_addr = (uint32_t)__cvta_generic_to_shared(s_in);
-        StreamCursor c;
-        c.init<kPadded>(in_addr, pos);
+        StreamCursorT<kRaw> c;
+        c.template init<kPadded>(in_addr, pos);
         uint32_t ns = t.root_ns, tb = t.addr;
         const uint32_t root_tb = t.addr;
         uint32_t acc = 0;  // (kEmit) symbols not stored yet: the low out_addr & 3 bytes
@@ -672,63 +680,71 @@ __device__ __forceinline__ SpanS decode_span_lean(
 #pragma unroll
                 for (int step = 0; step < kUnifiedSteps; ++step) {
                     if (kEmit) {
-                        asm volatile(
-                            "{\n\t"
-                            ".reg .pred c, w;\n\t"
-                            ".reg .b32 win, idx, adr, x, u, t, sh, lo, sp, no, wadr;\n\t"
-                            "shf.l.wrap.b32 win, %2, %1, %0;\n\t"
-                            "shf.r.wrap.b32 idx, win, 0, %7;\n\t"
-                            "mad.lo.u32 adr, idx, 8, %8;\n\t"
-                            "ld.shared.v2.u32 {x, %7}, [adr];\n\t"
-                            "and.b32 %8, %7, 0x00ffffe0;\n\t"
-                            "shr.u32 u, %7, 24;\n\t"
-                            "add.u32 %0, %0, u;\n\t"
-                            "and.b32 t, x, 0xffff;\n\t"
-                            "shl.b32 sh, %6, 3;\n\t"
-                            "shf.l.wrap.b32 lo, 0, t, sh;\n\t"
-                            "shf.l.wrap.b32 sp, t, 0, sh;\n\t"
-                            "or.b32 lo, lo, %9;\n\t"
-                            "shr.u32 u, x, 30;\n\t"
-                            "add.u32 no, %6, u;\n\t"
-                            "xor.b32 u, no, %6;\n\t"
-                            "and.b32 u, u, 4;\n\t"
-                            "setp.ne.u32 w, u, 0;\n\t"
-                            "and.b32 wadr, %6, 0xfffffffc;\n\t"
-                            "@w st.shared.u32 [wadr], lo;\n\t"
-                            "selp.b32 %9, sp, lo, w;\n\t"
-                            "mov.b32 %6, no;\n\t"
-                            "setp.ge.s32 c, %0, %5;\n\t"
-                            "@c mov.b32 %1, %2;\n\t"
-                            "@c mov.b32 %2, %3;\n\t"
-                            "@c ld.shared.u32 %3, [%4];\n\t"
-                            "@c add.u32 %4, %4, 4;\n\t"
-                            "@c add.s32 %5, %5, 32;\n\t"
-                            "}"
-                            : "+r"(pos), "+r"(c.w0), "+r"(c.w1), "+r"(c.w2), "+r"(c.wa), "+r"(c.limit), "+r"(out_addr), "+r"(ns), "+r"(tb), "+r"(acc)
-                            :
+
+#define HB_STEP_ASM(SWAP) asm volatile( \
+                            "{\n\t" \
+                            ".reg .pred c, w;\n\t" \
+                            ".reg .b32 win, idx, adr, x, u, t, sh, lo, sp, no, wadr;\n\t" \
+                            "shf.l.wrap.b32 win, %2, %1, %0;\n\t" \
+                            "shf.r.wrap.b32 idx, win, 0, %7;\n\t" \
+                            "mad.lo.u32 adr, idx, 8, %8;\n\t" \
+                            "ld.shared.v2.u32 {x, %7}, [adr];\n\t" \
+                            "and.b32 %8, %7, 0x00ffffe0;\n\t" \
+                            "shr.u32 u, %7, 24;\n\t" \
+                            "add.u32 %0, %0, u;\n\t" \
+                            "and.b32 t, x, 0xffff;\n\t" \
+                            "shl.b32 sh, %6, 3;\n\t" \
+                            "shf.l.wrap.b32 lo, 0, t, sh;\n\t" \
+                            "shf.l.wrap.b32 sp, t, 0, sh;\n\t" \
+                            "or.b32 lo, lo, %9;\n\t" \
+                            "shr.u32 u, x, 30;\n\t" \
+                            "add.u32 no, %6, u;\n\t" \
+                            "xor.b32 u, no, %6;\n\t" \
+                            "and.b32 u, u, 4;\n\t" \
+                            "setp.ne.u32 w, u, 0;\n\t" \
+                            "and.b32 wadr, %6, 0xfffffffc;\n\t" \
+                            "@w st.shared.u32 [wadr], lo;\n\t" \
+                            "selp.b32 %9, sp, lo, w;\n\t" \
+                            "mov.b32 %6, no;\n\t" \
+                            "setp.ge.s32 c, %0, %5;\n\t" \
+                            "@c mov.b32 %1, %2;\n\t" \
+                            "@c mov.b32 %2, %3;\n\t" \
+                            "@c ld.shared.u32 %3, [%4];\n\t" SWAP \
+                            "@c add.u32 %4, %4, 4;\n\t" \
+                            "@c add.s32 %5, %5, 32;\n\t" \
+                            "}" \
+                            : "+r"(pos), "+r"(c.w0), "+r"(c.w1), "+r"(c.w2), "+r"(c.wa), "+r"(c.limit), "+r"(out_addr), "+r"(ns), "+r"(tb), "+r"(acc) \
+                            : \
                             : "memory");
+                        if (kRaw) { HB_STEP_ASM("@c prmt.b32 %3, %3, 0, 0x0123;\n\t") } else { HB_STEP_ASM("") }
+#undef HB_STEP_ASM
+
                     } else {
-                        asm volatile(
-                            "{\n\t"
-                            ".reg .pred c;\n\t"
-                            ".reg .b32 win, idx, adr, x, u;\n\t"
-                            "shf.l.wrap.b32 win, %2, %1, %0;\n\t"
-                            "shf.r.wrap.b32 idx, win, 0, %6;\n\t"
-                            "mad.lo.u32 adr, idx, 8, %7;\n\t"
-                            "ld.shared.v2.u32 {x, %6}, [adr];\n\t"
-                            "and.b32 %7, %6, 0x00ffffe0;\n\t"
-                            "shr.u32 u, %6, 24;\n\t"
-                            "add.u32 %0, %0, u;\n\t"
-                            "setp.ge.s32 c, %0, %5;\n\t"
-                            "@c mov.b32 %1, %2;\n\t"
-                            "@c mov.b32 %2, %3;\n\t"
-                            "@c ld.shared.u32 %3, [%4];\n\t"
-                            "@c add.u32 %4, %4, 4;\n\t"
-                            "@c add.s32 %5, %5, 32;\n\t"
-                            "}"
-                            : "+r"(pos), "+r"(c.w0), "+r"(c.w1), "+r"(c.w2), "+r"(c.wa), "+r"(c.limit), "+r"(ns), "+r"(tb)
-                            :
+
+#define HB_STEP_ASM(SWAP) asm volatile( \
+                            "{\n\t" \
+                            ".reg .pred c;\n\t" \
+                            ".reg .b32 win, idx, adr, x, u;\n\t" \
+                            "shf.l.wrap.b32 win, %2, %1, %0;\n\t" \
+                            "shf.r.wrap.b32 idx, win, 0, %6;\n\t" \
+                            "mad.lo.u32 adr, idx, 8, %7;\n\t" \
+                            "ld.shared.v2.u32 {x, %6}, [adr];\n\t" \
+                            "and.b32 %7, %6, 0x00ffffe0;\n\t" \
+                            "shr.u32 u, %6, 24;\n\t" \
+                            "add.u32 %0, %0, u;\n\t" \
+                            "setp.ge.s32 c, %0, %5;\n\t" \
+                            "@c mov.b32 %1, %2;\n\t" \
+                            "@c mov.b32 %2, %3;\n\t" \
+                            "@c ld.shared.u32 %3, [%4];\n\t" SWAP \
+                            "@c add.u32 %4, %4, 4;\n\t" \
+                            "@c add.s32 %5, %5, 32;\n\t" \
+                            "}" \
+                            : "+r"(pos), "+r"(c.w0), "+r"(c.w1), "+r"(c.w2), "+r"(c.wa), "+r"(c.limit), "+r"(ns), "+r"(tb) \
+                            : \
                             : "memory");
+                        if (kRaw) { HB_STEP_ASM("@c prmt.b32 %3, %3, 0, 0x0123;\n\t") } else { HB_STEP_ASM("") }
+#undef HB_STEP_ASM
+
                     }
                 }
                 if (tb == t.trap_tb) {  // no code matches: leave the loops, the exact loop below redoes the span
@@ -748,68 +764,76 @@ __device__ __forceinline__ SpanS decode_span_lean(
                     // symbols are collected in `acc` (little-endian, out & 3 bytes pending) and leave as whole
                     // 32-bit words: a quarter of the stores of the byte-by-byte version, and those were 40 % of the
                     // kernel's shared-memory wavefronts (the decode phase is bound by them, not by issue slots)
-                    asm volatile(
-                        "{\n\t"
-                        ".reg .pred p, c, w;\n\t"
-                        ".reg .b32 win, idx, adr, x, u, t, sh, lo, sp, no, wadr;\n\t"
-                        "setp.lt.u32 p, %0, %10;\n\t"
-                        "setp.ne.or.u32 p, %8, %11, p;\n\t"
-                        "shf.l.wrap.b32 win, %2, %1, %0;\n\t"
-                        "shf.r.wrap.b32 idx, win, 0, %7;\n\t"
-                        "mad.lo.u32 adr, idx, 8, %8;\n\t"
-                        "mov.b32 x, 0;\n\t"
-                        "@p ld.shared.v2.u32 {x, %7}, [adr];\n\t"
-                        "and.b32 %8, %7, 0x00ffffe0;\n\t"
-                        "shr.u32 u, %7, 24;\n\t"
-                        "@p add.u32 %0, %0, u;\n\t"
-                        "and.b32 t, x, 0xffff;\n\t"
-                        "shl.b32 sh, %6, 3;\n\t"
-                        "shf.l.wrap.b32 lo, 0, t, sh;\n\t"
-                        "shf.l.wrap.b32 sp, t, 0, sh;\n\t"
-                        "or.b32 lo, lo, %9;\n\t"
-                        "shr.u32 u, x, 30;\n\t"
-                        "add.u32 no, %6, u;\n\t"
-                        "xor.b32 u, no, %6;\n\t"
-                        "and.b32 u, u, 4;\n\t"
-                        "setp.ne.u32 w, u, 0;\n\t"
-                        "and.b32 wadr, %6, 0xfffffffc;\n\t"
-                        "@w st.shared.u32 [wadr], lo;\n\t"
-                        "selp.b32 %9, sp, lo, w;\n\t"
-                        "mov.b32 %6, no;\n\t"
-                        "setp.ge.s32 c, %0, %5;\n\t"
-                        "@c mov.b32 %1, %2;\n\t"
-                        "@c mov.b32 %2, %3;\n\t"
-                        "@c ld.shared.u32 %3, [%4];\n\t"
-                        "@c add.u32 %4, %4, 4;\n\t"
-                        "@c add.s32 %5, %5, 32;\n\t"
-                        "}"
-                        : "+r"(pos), "+r"(c.w0), "+r"(c.w1), "+r"(c.w2), "+r"(c.wa), "+r"(c.limit), "+r"(out_addr), "+r"(ns), "+r"(tb), "+r"(acc)
-                        : "r"(pair_end), "r"(root_tb)
+
+#define HB_STEP_ASM(SWAP) asm volatile( \
+                        "{\n\t" \
+                        ".reg .pred p, c, w;\n\t" \
+                        ".reg .b32 win, idx, adr, x, u, t, sh, lo, sp, no, wadr;\n\t" \
+                        "setp.lt.u32 p, %0, %10;\n\t" \
+                        "setp.ne.or.u32 p, %8, %11, p;\n\t" \
+                        "shf.l.wrap.b32 win, %2, %1, %0;\n\t" \
+                        "shf.r.wrap.b32 idx, win, 0, %7;\n\t" \
+                        "mad.lo.u32 adr, idx, 8, %8;\n\t" \
+                        "mov.b32 x, 0;\n\t" \
+                        "@p ld.shared.v2.u32 {x, %7}, [adr];\n\t" \
+                        "and.b32 %8, %7, 0x00ffffe0;\n\t" \
+                        "shr.u32 u, %7, 24;\n\t" \
+                        "@p add.u32 %0, %0, u;\n\t" \
+                        "and.b32 t, x, 0xffff;\n\t" \
+                        "shl.b32 sh, %6, 3;\n\t" \
+                        "shf.l.wrap.b32 lo, 0, t, sh;\n\t" \
+                        "shf.l.wrap.b32 sp, t, 0, sh;\n\t" \
+                        "or.b32 lo, lo, %9;\n\t" \
+                        "shr.u32 u, x, 30;\n\t" \
+                        "add.u32 no, %6, u;\n\t" \
+                        "xor.b32 u, no, %6;\n\t" \
+                        "and.b32 u, u, 4;\n\t" \
+                        "setp.ne.u32 w, u, 0;\n\t" \
+                        "and.b32 wadr, %6, 0xfffffffc;\n\t" \
+                        "@w st.shared.u32 [wadr], lo;\n\t" \
+                        "selp.b32 %9, sp, lo, w;\n\t" \
+                        "mov.b32 %6, no;\n\t" \
+                        "setp.ge.s32 c, %0, %5;\n\t" \
+                        "@c mov.b32 %1, %2;\n\t" \
+                        "@c mov.b32 %2, %3;\n\t" \
+                        "@c ld.shared.u32 %3, [%4];\n\t" SWAP \
+                        "@c add.u32 %4, %4, 4;\n\t" \
+                        "@c add.s32 %5, %5, 32;\n\t" \
+                        "}" \
+                        : "+r"(pos), "+r"(c.w0), "+r"(c.w1), "+r"(c.w2), "+r"(c.wa), "+r"(c.limit), "+r"(out_addr), "+r"(ns), "+r"(tb), "+r"(acc) \
+                        : "r"(pair_end), "r"(root_tb) \
                         : "memory");
+                    if (kRaw) { HB_STEP_ASM("@c prmt.b32 %3, %3, 0, 0x0123;\n\t") } else { HB_STEP_ASM("") }
+#undef HB_STEP_ASM
+
                 } else {
-                    asm volatile(
-                        "{\n\t"
-                        ".reg .pred p, c;\n\t"
-                        ".reg .b32 win, idx, adr, x, u;\n\t"
-                        "setp.lt.u32 p, %0, %8;\n\t"
-                        "setp.ne.or.u32 p, %7, %9, p;\n\t"
-                        "shf.l.wrap.b32 win, %2, %1, %0;\n\t"
-                        "shf.r.wrap.b32 idx, win, 0, %6;\n\t"
-                        "mad.lo.u32 adr, idx, 8, %7;\n\t"
-                        "@p ld.shared.v2.u32 {x, %6}, [adr];\n\t"
-                        "and.b32 %7, %6, 0x00ffffe0;\n\t"
-                        "shr.u32 u, %6, 24;\n\t"
-                        "@p add.u32 %0, %0, u;\n\t"
-                        "setp.ge.s32 c, %0, %5;\n\t"
-                        "@c mov.b32 %1, %2;\n\t"
-                        "@c mov.b32 %2, %3;\n\t"
-                        "@c ld.shared.u32 %3, [%4];\n\t"
-                        "@c add.u32 %4, %4, 4;\n\t"
-                        "@c add.s32 %5, %5, 32;\n\t"
-                        "}"
-                        : "+r"(pos), "+r"(c.w0), "+r"(c.w1), "+r"(c.w2), "+r"(c.wa), "+r"(c.limit), "+r"(ns), "+r"(tb)
-                        : "r"(pair_end), "r"(root_tb)
+
+#define HB_STEP_ASM(SWAP) asm volatile( \
+                        "{\n\t" \
+                        ".reg .pred p, c;\n\t" \
+                        ".reg .b32 win, idx, adr, x, u;\n\t" \
+                        "setp.lt.u32 p, %0, %8;\n\t" \
+                        "setp.ne.or.u32 p, %7, %9, p;\n\t" \
+                        "shf.l.wrap.b32 win, %2, %1, %0;\n\t" \
+                        "shf.r.wrap.b32 idx, win, 0, %6;\n\t" \
+                        "mad.lo.u32 adr, idx, 8, %7;\n\t" \
+                        "@p ld.shared.v2.u32 {x, %6}, [adr];\n\t" \
+                        "and.b32 %7, %6, 0x00ffffe0;\n\t" \
+                        "shr.u32 u, %6, 24;\n\t" \
+                        "@p add.u32 %0, %0, u;\n\t" \
+                        "setp.ge.s32 c, %0, %5;\n\t" \
+                        "@c mov.b32 %1, %2;\n\t" \
+                        "@c mov.b32 %2, %3;\n\t" \
+                        "@c ld.shared.u32 %3, [%4];\n\t" SWAP \
+                        "@c add.u32 %4, %4, 4;\n\t" \
+                        "@c add.s32 %5, %5, 32;\n\t" \
+                        "}" \
+                        : "+r"(pos), "+r"(c.w0), "+r"(c.w1), "+r"(c.w2), "+r"(c.wa), "+r"(c.limit), "+r"(ns), "+r"(tb) \
+                        : "r"(pair_end), "r"(root_tb) \
                         : "memory");
+                    if (kRaw) { HB_STEP_ASM("@c prmt.b32 %3, %3, 0, 0x0123;\n\t") } else { HB_STEP_ASM("") }
+#undef HB_STEP_ASM
+
                 }
             }
             if (tb == t.trap_tb) {  // no code matches: leave the loop, the exact loop below redoes the span
@@ -835,7 +859,7 @@ __device__ __forceinline__ SpanS decode_span_lean(
             }
             pos = pos0;
             out_addr = out0;
-            c.init<kPadded>(in_addr, pos);
+            c.template init<kPadded>(in_addr, pos);
         } else if (kEmit && (out_addr & 3u)) {
             if (kInPlace) {  // the symbols still in `acc`, and not a byte more
                 for (uint32_t k = 0; k < (out_addr & 3u); ++k) sts_u8((out_addr & ~3u) + k, acc >> (8 * k));
@@ -966,6 +990,36 @@ __device__ __forceinline__ void dec_bar_sync(uint32_t id) { asm volatile("bar.sy
 constexpr uint32_t kDecMaxRow = 4096;        // a staged string decodes to at most this many bytes
 constexpr uint32_t kDecRowSlack = 8;         // spare bytes per row (alignment, the emitter's look-ahead byte)
 
+// HB_DEC_TMA_STAGE: the tile's encoded bytes come into the stage by ONE bulk copy (cp.async.bulk global -> shared,
+// completion on an mbarrier: the TMA unit moves them while the team sorts its strings) instead of the team's own
+// 128-bit loads, byte permutes and stores; the stage then holds the bytes as they are in memory and the decoder
+// swaps a word when it fetches it (one PRMT per 32 consumed bits). Not for the framed decoder.
+#ifndef HB_DEC_TMA_STAGE
+#define HB_DEC_TMA_STAGE 1
+#endif
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_copy_to_shared(uint32_t dst, const void *src, uint32_t bytes, uint32_t mbar) {
+    // (the stage was read and written through the generic proxy by the previous tile)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "HB_MBAR_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra HB_MBAR_WAIT;\n\t"
+        "}" ::"r"(mbar), "r"(parity)
+        : "memory");
+}
+
 struct DecBatchArgs {
     BatchView b;
     const uint32_t *lut;   // 32-bit table in global memory (the rare tiles that do not fit the stage)
@@ -1082,6 +1136,7 @@ struct DecTeamShared {
     uint32_t tile, next, fits, total;
     uint32_t hand_tile[2];                 // workers -> scout, by hand-off parity
     uint64_t hand_prefix[2];               // scout -> workers
+    uint64_t mbar;                         // HB_DEC_TMA_STAGE: completion of the stage's bulk copy
 };
 
 template <bool kFramed>
@@ -1113,6 +1168,10 @@ __global__ void __launch_bounds__(kDecTeams * kDecBlock, 1) decode_batch_kernel(
     const Lut2 lut2 = lut2_load(reinterpret_cast<uint2 *>(s_lut), a.lut2, a.lut2_count, a.root_bits, a.lut2_trap);
     const uint32_t lane = lane_id(), warp = tid >> 5;
     const BatchView &b = a.b;
+    constexpr bool kRaw = HB_DEC_TMA_STAGE != 0 && !kFramed;
+    const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&sh.mbar);
+    if (kRaw && tid == 0) mbar_init(mbar, 1);
+    uint32_t stage_phase = 0;  // parity of the bulk copy the team waits for next
     __syncthreads();  // the LUT is in place
     // ================================ scout =====================================================================
     // The ninth warp resolves where the tile's output starts — the sum of the symbol counts of ALL tiles before it
@@ -1173,6 +1232,13 @@ __global__ void __launch_bounds__(kDecTeams * kDecBlock, 1) decode_batch_kernel(
         // row i starts at 4 * ceil(2 * offset / min_len) + slack * i: never before the end of row i - 1
         const uint64_t rows_need = 4 * ((2 * (byte1 - byte0) + a.min_len - 1) / a.min_len) + (uint64_t)kDecRowSlack * (nitems + 1);
         bool fits = nwords64 <= a.stage_words && rows_need <= a.rows_bytes;
+        // (kRaw) The whole 16-byte pieces of the tile's bytes are requested NOW, as one bulk copy: they arrive while
+        // the team builds its string table and sorts. (A tile that turns out to hold a string too long for a row is
+        // not decoded from the stage; the copy is awaited all the same.)
+        const bool bulk = kRaw && fits && (nwords64 >> 2) != 0;
+        if (bulk && tid == 0)
+            bulk_copy_to_shared((uint32_t)__cvta_generic_to_shared(s_in), reinterpret_cast<const void *>(addr0 - lead),
+                                16u * (uint32_t)(nwords64 >> 2), mbar);
         for (uint32_t it = tid; it < nitems; it += kDecThreads) {
             const uint64_t in0 = b.in_offsets[item0 + it];
             uint64_t len = b.in_offsets[item0 + it + 1] - in0;
@@ -1195,22 +1261,27 @@ __global__ void __launch_bounds__(kDecTeams * kDecBlock, 1) decode_batch_kernel(
         dec_worker_sync(team);
         const bool staged = fits && s_fits != 0;
         if (staged) {
-            // ---- stage the tile's encoded bytes as big-endian words -------------------------------------------
             const uint32_t nwords = (uint32_t)nwords64;
-            const uint32_t nquads = nwords >> 2;  // whole 128-bit loads; the ragged end goes word by word
-            const uint4 *g4 = reinterpret_cast<const uint4 *>(addr0 - lead);
-            for (uint32_t j = tid; j < nquads; j += kDecThreads) {
-                const uint4 v = __ldg(g4 + j);
-                uint4 o;
-                o.x = __byte_perm(v.x, 0, 0x0123);
-                o.y = __byte_perm(v.y, 0, 0x0123);
-                o.z = __byte_perm(v.z, 0, 0x0123);
-                o.w = __byte_perm(v.w, 0, 0x0123);
-                reinterpret_cast<uint4 *>(s_in)[j] = o;
-            }
+            const uint32_t nquads = nwords >> 2;  // whole 128-bit pieces; the ragged end goes word by word
             const uint32_t *gw = reinterpret_cast<const uint32_t *>(addr0 - lead);
-            for (uint32_t j = 4 * nquads + tid; j < nwords; j += kDecThreads)
-                s_in[j] = __byte_perm(__ldg(gw + j), 0, 0x0123);
+            if (kRaw) {
+                // ---- (the bulk copy is under way) the ragged end, bytes as they are in memory -------------------------
+                for (uint32_t j = 4 * nquads + tid; j < nwords; j += kDecThreads) s_in[j] = __ldg(gw + j);
+            } else {
+                // ---- stage the tile's encoded bytes as big-endian words -------------------------------------------
+                const uint4 *g4 = reinterpret_cast<const uint4 *>(addr0 - lead);
+                for (uint32_t j = tid; j < nquads; j += kDecThreads) {
+                    const uint4 v = __ldg(g4 + j);
+                    uint4 o;
+                    o.x = __byte_perm(v.x, 0, 0x0123);
+                    o.y = __byte_perm(v.y, 0, 0x0123);
+                    o.z = __byte_perm(v.z, 0, 0x0123);
+                    o.w = __byte_perm(v.w, 0, 0x0123);
+                    reinterpret_cast<uint4 *>(s_in)[j] = o;
+                }
+                for (uint32_t j = 4 * nquads + tid; j < nwords; j += kDecThreads)
+                    s_in[j] = __byte_perm(__ldg(gw + j), 0, 0x0123);
+            }
             if (tid < 2) s_in[nwords + tid] = 0;
         }
         if (warp == 0) {
@@ -1235,6 +1306,10 @@ __global__ void __launch_bounds__(kDecTeams * kDecBlock, 1) decode_batch_kernel(
         }
         dec_worker_sync(team);
 
+        if (kRaw && bulk) {  // the stage's bytes have landed
+            mbar_wait(mbar, stage_phase);
+            stage_phase ^= 1u;
+        }
         HB_PHASE_MARK(0);  // ticket, string table, staging, sort
         // ---- decode (staged: once, into the rows; otherwise: count) ------------------------------------------
         for (uint32_t g = warp < (uint32_t)kDecPullWarps ? warp : ngroups; g < ngroups;) {
@@ -1260,7 +1335,7 @@ __global__ void __launch_bounds__(kDecTeams * kDecBlock, 1) decode_batch_kernel(
                     }
                 } else if (staged) {
                     const uint32_t ib = s_start[it], ie = ib + nbytes * 8;
-                    const SpanS r = decode_span_lean<true, false, false>(s_in, lut2, a.root_bits, ib, ie, ie, rows_addr + s_row[it]);
+                    const SpanS r = decode_span_lean<true, false, false, false, kRaw>(s_in, lut2, a.root_bits, ib, ie, ie, rows_addr + s_row[it]);
                     cbits = r.pos - ib;
                     nsym = r.nsym;
                     term = r.term;
