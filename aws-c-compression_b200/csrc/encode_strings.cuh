@@ -218,7 +218,9 @@ __global__ void __launch_bounds__(kBitsThreads, 1024 / kBitsThreads) str_bits_ke
     __shared__ __align__(16) uint8_t s_lentab[256];
     __shared__ __align__(16) uint32_t s_pre[kBitsTileVecs][8];  // per vector: inclusive prefix after byte 2j | after byte 2j+1 << 16
     __shared__ uint32_t s_vex[kBitsTileVecs + 1];               // exclusive prefix over the vectors; [nvec] = the tile's total
-    __shared__ uint32_t s_wsum[kBitsThreads / 32];
+    // (16-byte aligned: the compiler reads the warp sums as vectors, and a vector that started in s_vex's last word
+    // made compute-sanitizer's racecheck flag that word — written in the same phase, never used by the reader)
+    __shared__ __align__(16) uint32_t s_wsum[kBitsThreads / 32];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (uint32_t i = tid; i < 256; i += kBitsThreads) s_lentab[i] = (uint8_t)enc_table[i].y;
 

@@ -21,3 +21,12 @@ if [[ " $* " != *" noncu "* ]]; then
       python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-parity --workload stream > /dev/null 2>&1
   ls -la $O
 fi
+if [[ " $* " == *" sanitizer "* ]]; then
+  # compute-sanitizer over a subset of the GPU parity suite (memcheck: every access; racecheck: shared-memory hazards)
+  timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_batch.py -m gpu -x -q \
+      -k "golden or rfc7541 or committed or random_batches or single_stream or empty" > $O/sanitizer_memcheck.txt 2>&1
+  echo "memcheck exit $?" >> $O/sanitizer_memcheck.txt; tail -4 $O/sanitizer_memcheck.txt
+  timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_batch.py -m gpu -x -q \
+      -k "golden or rfc7541 or committed" > $O/sanitizer_racecheck.txt 2>&1
+  echo "racecheck exit $?" >> $O/sanitizer_racecheck.txt; tail -4 $O/sanitizer_racecheck.txt
+fi
