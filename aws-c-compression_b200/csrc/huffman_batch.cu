@@ -174,6 +174,31 @@ int device_call_end(aws_huffman_batch_ctx *ctx, cudaStream_t st, int rc) {
     return rc;
 }
 
+// The dynamic shared-memory limit belongs to a kernel ON A DEVICE, not to a context; tables differ in size. It is
+// raised when a launch needs more than was ever asked for on that device (not on every call: the host path issues
+// one call per 8 MiB sub-batch).
+template <typename K>
+int ensure_dynamic_smem(K kernel, int device, size_t bytes) {
+    struct Seen {
+        const void *kernel;
+        size_t bytes[16];
+    };
+    static Seen seen[16] = {};  // (a handful of kernels ask; keyed by the kernel's address, then by device)
+    const void *key = reinterpret_cast<const void *>(kernel);
+    for (Seen &e : seen) {
+        if (e.kernel != key && e.kernel != nullptr) continue;
+        e.kernel = key;
+        size_t &cur = e.bytes[device & 15];
+        if (bytes > cur) {
+            HB_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            cur = bytes;
+        }
+        return AWS_OP_SUCCESS;
+    }
+    HB_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return AWS_OP_SUCCESS;
+}
+
 constexpr uint32_t kLutRootBits = 12;
 constexpr uint32_t kLutSubBits = 8;
 constexpr uint32_t kLutMaxSmemEntries = 8192;  // 32 KiB
@@ -491,8 +516,8 @@ int decode_batch_fast(
     a.num_tiles = (uint32_t)num_tiles;
     const size_t team_bytes = ((stage_bytes + 15) & ~size_t(15)) + rows_bytes + 64;
     const size_t smem = lut_bytes + kDecTeams * team_bytes;
-    HB_CUDA_TRY(cudaFuncSetAttribute(
-        framed ? decode_batch_kernel<true> : decode_batch_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (framed ? ensure_dynamic_smem(decode_batch_kernel<true>, ctx->device, smem) : ensure_dynamic_smem(decode_batch_kernel<false>, ctx->device, smem))
+        return AWS_OP_ERR;
     const unsigned blocks = (unsigned)std::min<uint64_t>((num_tiles + kDecTeams - 1) / kDecTeams, (uint64_t)ctx->sm_count);
     if (framed) decode_batch_kernel<true><<<blocks, kDecTeams * kDecBlock, smem, stream>>>(a);
     else decode_batch_kernel<false><<<blocks, kDecTeams * kDecBlock, smem, stream>>>(a);
@@ -671,7 +696,7 @@ int decode_stream_fast(
         f.ticket = reinterpret_cast<uint32_t *>(f.tile_rec + f.num_tiles);
         f.fail = f.ticket + 2;
         a.gate = f.fail;
-        HB_CUDA_TRY(cudaFuncSetAttribute(stream_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem));
+        if (ensure_dynamic_smem(stream_fused_kernel, ctx->device, fused_smem)) return AWS_OP_ERR;
         const unsigned blocks = (unsigned)std::min<uint64_t>((f.num_tiles + kStreamTeams - 1) / kStreamTeams, (uint64_t)ctx->sm_count);
         stream_fused_kernel<<<blocks, kStreamTeams * kStreamTeamThreads, fused_smem, stream>>>(f);
         stream_fused_verify_kernel<<<(unsigned)std::min<uint64_t>((f.num_tiles + 255) / 256, 1024), 256, 0, stream>>>(f);
@@ -681,8 +706,8 @@ int decode_stream_fast(
 
     // ---- multi-kernel path (alone, or gated behind the fused kernel's fail flag) ----------------------------------
     HB_CUDA_TRY(cudaMemsetAsync(a.control, 0xff, 2 * sizeof(uint64_t), stream));
-    HB_CUDA_TRY(cudaFuncSetAttribute(stream_sync_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_staged));
-    HB_CUDA_TRY(cudaFuncSetAttribute(stream_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_staged));
+    if (ensure_dynamic_smem(stream_sync_kernel, ctx->device, smem_staged) || ensure_dynamic_smem(stream_write_kernel, ctx->device, smem_staged))
+        return AWS_OP_ERR;
     // a gated launch that finds the flag clear costs a few microseconds: keep those grids small
     const uint64_t cap_wide = fused ? (uint64_t)ctx->sm_count * 4 : (uint64_t)ctx->sm_count * 12;
     const uint64_t cap_flat = fused ? (uint64_t)ctx->sm_count * 4 : (uint64_t)ctx->sm_count * 8;
