@@ -136,7 +136,7 @@ struct aws_huffman_batch_ctx {
     int str_blocks_per_sm[3] = {0, 0, 0};  // str_bits_kernel, str_pack_kernel, str_scan_kernel
     // staging for the host entry points
     GrowBuf s_in, s_in_off, s_out, s_out_off, s_caps, s_status, s_consumed, s_ovf_pattern, s_ovf_bits, s_left_bits,
-        s_left_num;
+        s_left_num, s_chain;
     // HPACK string literals (hpack_literals.cuh): packed payloads between the framing and the codec, per-item plans
     GrowBuf hp_pay, hp_pay_off, hp_dec, hp_dec_off, hp_huff, hp_prefix, hp_lens, hp_pay_lens, hp_dec_status, hp_left_bits,
         hp_left_num, hp_status;
@@ -769,6 +769,34 @@ __global__ void add_base_kernel(uint64_t *offsets, uint64_t count, uint64_t base
     if (i < count) offsets[i] += base;
 }
 
+// Sub-batch j of the pipelined host path leaves the device WITHOUT the host knowing its size: this kernel reads the
+// sub-batch's size and the running output position (written by sub-batch j - 1's instance; the streams are ordered
+// by an event), publishes the next position, rebases the sub-batch's packed offsets and copies its payload straight
+// into the caller's pinned buffer (`dst`: the device's alias of it) with 128-bit stores.
+constexpr int kChainBlocks = 96, kChainThreads = 256;
+constexpr uint32_t kChainSegment = 16 * 1024;  // bytes a block moves per turn (multiple of 16)
+__global__ void __launch_bounds__(kChainThreads) d2h_chain_kernel(
+    const uint8_t *src, uint64_t *out_off, uint64_t nj, const uint64_t *base_in, uint64_t *base_out, uint8_t *dst,
+    uint64_t capacity, uint32_t *overflow) {
+    const uint64_t base = base_in ? *base_in : 0;
+    const uint64_t total = out_off[nj];
+    const bool fits = base + total <= capacity;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        *base_out = base + total;
+        if (!fits) *overflow = 1u;
+    }
+    if (fits) {
+        for (uint64_t seg = (uint64_t)blockIdx.x * kChainSegment; seg < total; seg += (uint64_t)gridDim.x * kChainSegment)
+            hb::block_copy_realign(src + seg, dst + base + seg, (uint32_t)min((uint64_t)kChainSegment, total - seg), threadIdx.x, kChainThreads);
+    }
+    if (base)
+        for (uint64_t i = (uint64_t)blockIdx.x * kChainThreads + threadIdx.x; i < nj; i += (uint64_t)gridDim.x * kChainThreads)
+            out_off[i] += base;
+}
+
+template <typename T>
+T *mapped_alias(T *p, uint64_t size);
+
 int lane_prepare(Lane &lane) {
     if (lane.stream) return AWS_OP_SUCCESS;
     HB_CUDA_TRY(cudaStreamCreateWithFlags(&lane.stream, cudaStreamNonBlocking));
@@ -780,7 +808,8 @@ int lane_prepare(Lane &lane) {
 
 constexpr uint64_t kZeroCopyMinBytes = 4096;          // pinned payload buffers: kernels work on them in place
 constexpr uint64_t kPipelineMinBytes = 8ull << 20;   // below this one shot is as good
-constexpr uint64_t kPipelineShardBytes = 8ull << 20;  // measured best on PCIe Gen5 x16 (tools/e2e_sweep.sh)
+constexpr uint64_t kPipelineShardBytes = 12ull << 20;  // measured on PCIe Gen5 x16: 4 / 6 / 8 / 12 / 16 MiB: 53.2 / 57.0 / 58.3 / 60.4 / 59.6 GB/s
+                                                       // end to end (round 1, slower kernels: 8 MiB)
 
 // Packed layout with many items: the batch is cut into sub-batches (contiguous item ranges balanced by
 // bytes) that flow through kLanes lanes, so the host->device copy of one sub-batch, the kernels of the
@@ -811,13 +840,31 @@ int run_host_batch_pipelined(aws_huffman_batch_ctx *ctx, const aws_huffman_batch
     const uint32_t max_len = std::max<uint32_t>(1, ctx->tables.max_len);
     const uint32_t min_len = std::max<uint32_t>(1, ctx->tables.min_len);
     // a sub-batch is retired `depth` issues after it was issued; more lanes than that keep re-use from waiting
-    size_t depth = 2, lanes_used = 5;
+    size_t depth = 1, lanes_used = 4;  // (round 2, 12 MiB sub-batches: depth 1 / 4 lanes 60.9, depth 2 / 5 lanes 59.7, depth 1 / 3 lanes 59.6 GB/s)
     if (const char *d = getenv("AWS_HUFFMAN_BATCH_PIPE_DEPTH")) depth = std::min<size_t>(6, std::max(1, atoi(d)));
     if (const char *l = getenv("AWS_HUFFMAN_BATCH_PIPE_LANES")) lanes_used = std::min<size_t>(hb_host::kLanes, std::max(2, atoi(l)));
     lanes_used = std::max(lanes_used, depth + 2);
     lanes_used = std::min<size_t>(lanes_used, hb_host::kLanes);
     uint64_t base_out = 0;
     bool overflow = false;
+    // CHAINED mode (opt-in: AWS_HUFFMAN_BATCH_CHAIN=1 and a pinned output buffer): the host never learns a sub-batch's size
+    // while the call runs. A small kernel behind each sub-batch's codec kernels (d2h_chain_kernel) reads the size on the
+    // device, takes the running output position from its predecessor (streams ordered by an event), and writes the
+    // payload straight into the caller's buffer; the fixed-size arrays follow by ordinary copies. No
+    // cudaEventSynchronize per sub-batch, no copy that waits for the host to have seen a size, no drain of late
+    // sub-batches at the end. Correct (tests/test_gpu_multi.py) and MEASURED SLOWER than the copy engines: 53.6 GB/s end
+    // to end against 60.4 on the 1M-string batch (4 / 6 / 8 lanes: 56.5 / 53.6 / 48 GB/s: the more sub-batches in
+    // flight, the worse — kernel-issued PCIe writes hold their SMs while the copy engines work for free). Round 1
+    // measured the same for whole kernels working on pinned buffers; it holds for a dedicated copy kernel too.
+    uint8_t *const zout = getenv("AWS_HUFFMAN_BATCH_CHAIN") ? mapped_alias(b->out, b->out_capacity) : nullptr;
+    const bool chained = zout != nullptr;
+    uint64_t *chain = nullptr;      // [0 .. shards]: output position before sub-batch j; [shards + 1]: overflow flag
+    cudaEvent_t prev_copied = nullptr;
+    if (chained) {
+        HB_CUDA_TRY(ctx->s_chain.reserve((shards + 2) * sizeof(uint64_t)));
+        chain = ctx->s_chain.as<uint64_t>();
+        HB_CUDA_TRY(cudaMemsetAsync(chain + shards + 1, 0, sizeof(uint64_t), ctx->lanes[0].stream));
+    }
 
     auto issue = [&](size_t j) -> int {
         Lane &lane = ctx->lanes[j % lanes_used];
@@ -867,6 +914,38 @@ int run_host_batch_pipelined(aws_huffman_batch_ctx *ctx, const aws_huffman_batch
         if ((encode ? encode_on_device(ctx, lane.scratch, v, bytes_in, lane.stream)
                     : decode_on_device(ctx, lane.scratch, v, bytes_in, lane.stream)) != AWS_OP_SUCCESS)
             return AWS_OP_ERR;
+        if (chained) {
+            cudaStream_t st = lane.stream;
+            if (prev_copied) HB_CUDA_TRY(cudaStreamWaitEvent(st, prev_copied, 0));
+            d2h_chain_kernel<<<kChainBlocks, kChainThreads, 0, st>>>(
+                lane.out.as<uint8_t>(), lane.out_off.as<uint64_t>(), nj, j ? chain + j : nullptr, chain + j + 1, zout,
+                b->out_capacity, reinterpret_cast<uint32_t *>(chain + shards + 1));
+            ++ctx->launches;
+            HB_CUDA_TRY(cudaGetLastError());
+            HB_CUDA_TRY(cudaEventRecord(lane.kernels_done, st));
+            prev_copied = lane.kernels_done;
+            HB_CUDA_TRY(cudaMemcpyAsync(b->out_offsets + a, lane.out_off.ptr, nj * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+            if (b->out_lens)
+                HB_CUDA_TRY(cudaMemcpyAsync(b->out_lens + a, lane.lens.ptr, nj * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+            if (b->status)
+                HB_CUDA_TRY(cudaMemcpyAsync(b->status + a, lane.status.ptr, nj * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            if (b->consumed)
+                HB_CUDA_TRY(cudaMemcpyAsync(b->consumed + a, lane.consumed.ptr, nj * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+            if (encode) {
+                if (b->overflow_pattern)
+                    HB_CUDA_TRY(cudaMemcpyAsync(b->overflow_pattern + a, lane.aux32.ptr, nj * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+                if (b->overflow_num_bits)
+                    HB_CUDA_TRY(cudaMemcpyAsync(b->overflow_num_bits + a, lane.aux8.ptr, nj, cudaMemcpyDeviceToHost, st));
+            } else {
+                if (b->leftover_working_bits)
+                    HB_CUDA_TRY(cudaMemcpyAsync(b->leftover_working_bits + a, lane.aux64.ptr, nj * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+                if (b->leftover_num_bits)
+                    HB_CUDA_TRY(cudaMemcpyAsync(b->leftover_num_bits + a, lane.aux8.ptr, nj, cudaMemcpyDeviceToHost, st));
+            }
+            HB_CUDA_TRY(cudaEventRecord(lane.retired, st));
+            lane.in_flight = true;
+            return AWS_OP_SUCCESS;
+        }
         HB_CUDA_TRY(cudaMemcpyAsync(
             lane.h_total, lane.out_off.as<uint64_t>() + nj, sizeof(uint64_t), cudaMemcpyDeviceToHost, lane.stream));
         HB_CUDA_TRY(cudaEventRecord(lane.kernels_done, lane.stream));
@@ -924,8 +1003,10 @@ int run_host_batch_pipelined(aws_huffman_batch_ctx *ctx, const aws_huffman_batch
         }
         (void)cudaGetLastError();
     };
+    if (chained) depth = 0;  // (nothing to retire: a sub-batch is complete once issued)
+    if (chained && !getenv("AWS_HUFFMAN_BATCH_PIPE_LANES")) lanes_used = 6;  // (a lane is re-used only when everything of its last sub-batch has left)
     for (size_t j = 0; j < shards + depth; ++j) {
-        if ((j < shards && issue(j)) || (j >= depth && j - depth < shards && retire(j - depth))) {
+        if ((j < shards && issue(j)) || (!chained && j >= depth && j - depth < shards && retire(j - depth))) {
             const int err = aws_last_error();
             drain();
             return aws_raise_error(err ? err : AWS_ERROR_COMPRESSION_DEVICE_FAILURE);
@@ -934,6 +1015,12 @@ int run_host_batch_pipelined(aws_huffman_batch_ctx *ctx, const aws_huffman_batch
     for (Lane &lane : ctx->lanes) {
         if (lane.in_flight) HB_CUDA_TRY(cudaEventSynchronize(lane.retired));
         lane.in_flight = false;
+    }
+    if (chained) {
+        uint64_t tail[2] = {0, 0};  // the output position behind the last sub-batch, the overflow flag
+        HB_CUDA_TRY(cudaMemcpy(tail, chain + shards, sizeof(tail), cudaMemcpyDeviceToHost));
+        base_out = tail[0];
+        overflow = tail[1] != 0;
     }
     b->out_offsets[n] = base_out;
     if (overflow) return aws_raise_error(AWS_ERROR_SHORT_BUFFER);
@@ -1548,7 +1635,7 @@ void aws_huffman_batch_ctx_destroy(struct aws_huffman_batch_ctx *ctx) {
     if (ctx->d_lut2) cudaFree(ctx->d_lut2);
     GrowBuf *bufs[] = {&ctx->s_in,       &ctx->s_in_off,      &ctx->s_out,      &ctx->s_out_off,
                        &ctx->s_caps,     &ctx->s_status,      &ctx->s_consumed, &ctx->s_ovf_pattern,
-                       &ctx->s_ovf_bits, &ctx->s_left_bits,   &ctx->s_left_num, &ctx->hp_pay,
+                       &ctx->s_ovf_bits, &ctx->s_left_bits,   &ctx->s_left_num, &ctx->s_chain, &ctx->hp_pay,
                        &ctx->hp_pay_off, &ctx->hp_dec,        &ctx->hp_dec_off, &ctx->hp_huff,
                        &ctx->hp_prefix,  &ctx->hp_lens,       &ctx->hp_pay_lens, &ctx->hp_dec_status,
                        &ctx->hp_left_bits, &ctx->hp_left_num, &ctx->hp_status};

