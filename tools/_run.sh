@@ -1,4 +1,7 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -6
-python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-parity --workload hpack_batch 2>/dev/null | python -c "
-import json,sys; j=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('default e2e %.1f GB/s (%.2f ms)'%(j['e2e']['value'], j['e2e']['ms_per_step']))"
+V=$PWD/aws-c-compression_b200/lib/variants
+for v in default pk3a pk3b pk2c default pk3a pk3b; do
+  lib=""; [ "$v" != default ] && lib=$V/$v.so
+  AWS_HUFFMAN_B200_LIB=$lib python bench.py --steps 10 --warmup 3 --no-cpu-baseline --workload hpack_batch 2>/dev/null | python -c "
+import json,sys; j=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$v enc %.4f ms dec %.4f ms parity %s'%(j['encode_ms'], j['decode_ms'], j['parity_checked']['hpack_batch']['encoded_bytes_equal']))"
+done
