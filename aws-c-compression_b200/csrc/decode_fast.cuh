@@ -975,8 +975,9 @@ constexpr int kDecTeams = HB_DEC_TEAMS;      // teams per block (they share the 
 // Warps of a team that decode (the others wait at the barrier behind the decode phase, which costs nothing). The
 // phase cannot end before the tile's longest string does, so more lanes than the work needs only add contention
 // to every step of that string: the warps pull groups of 32 strings, longest first.
+// (measured, 1M strings of 8..256 B, 9 groups per tile: 8 / 7 / 6 / 5 pulling warps: 0.291 / 0.285 / 0.290 / 0.298 ms)
 #ifndef HB_DEC_PULL_WARPS
-#define HB_DEC_PULL_WARPS (HB_DEC_THREADS / 32)
+#define HB_DEC_PULL_WARPS (HB_DEC_THREADS / 32 - 1)
 #endif
 constexpr int kDecPullWarps = HB_DEC_PULL_WARPS;
 constexpr uint32_t kDecDone = 0xffffffffu;
@@ -1127,7 +1128,7 @@ struct DecTeamShared {
     uint32_t start[kDecItemsPerTile];   // first bit of the string in the stage
     uint32_t bytes[kDecItemsPerTile];   // encoded length
     uint32_t cnt[kDecItemsPerTile];     // symbols per string
-    uint32_t off[2][kDecItemsPerTile];  // exclusive offsets within the tile (this tile's and the pending one's)
+    uint32_t off[kDecItemsPerTile];     // exclusive offsets within the tile
     uint32_t row[kDecItemsPerTile];     // start of the string's row in the row area
     uint16_t perm[kDecItemsPerTile];    // strings in order of decreasing length
     uint8_t flag[kFramed ? kDecItemsPerTile : 4];  // framed: bit 0 raw payload, bit 1 malformed literal
@@ -1149,7 +1150,7 @@ __global__ void __launch_bounds__(kDecTeams * kDecBlock, 1) decode_batch_kernel(
     uint32_t (&s_start)[kDecItemsPerTile] = sh.start;
     uint32_t (&s_bytes)[kDecItemsPerTile] = sh.bytes;
     uint32_t (&s_cnt)[kDecItemsPerTile] = sh.cnt;
-    uint32_t (&s_off)[2][kDecItemsPerTile] = sh.off;
+    uint32_t (&s_off)[kDecItemsPerTile] = sh.off;
     uint32_t (&s_row)[kDecItemsPerTile] = sh.row;
     uint16_t (&s_perm)[kDecItemsPerTile] = sh.perm;
     auto &s_flag = sh.flag;
@@ -1402,11 +1403,11 @@ __global__ void __launch_bounds__(kDecTeams * kDecBlock, 1) decode_batch_kernel(
         {
             const uint64_t e0 = s_warp_sum[warp] + (incl - mine);  // exclusive, within the tile
             if (2 * tid < nitems) {
-                s_off[par][2 * tid] = (uint32_t)e0;
+                s_off[2 * tid] = (uint32_t)e0;
                 if (b.out_lens) b.out_lens[item0 + 2 * tid] = c0;
             }
             if (2 * tid + 1 < nitems) {
-                s_off[par][2 * tid + 1] = (uint32_t)(e0 + c0);
+                s_off[2 * tid + 1] = (uint32_t)(e0 + c0);
                 if (b.out_lens) b.out_lens[item0 + 2 * tid + 1] = c1;
             }
             if (tid == 0) s_next = kDecWarps;
@@ -1425,7 +1426,7 @@ __global__ void __launch_bounds__(kDecTeams * kDecBlock, 1) decode_batch_kernel(
                 for (uint32_t it = tid; it < nitems; it += kDecThreads) {
                     const uint32_t row = s_row[it];
 #ifndef HB_ABL_NO_COPY
-                    if ((row < front) == (phase == 0)) smem_copy_row(s_rows + row, s_dense + s_off[par][it], s_cnt[it]);
+                    if ((row < front) == (phase == 0)) smem_copy_row(s_rows + row, s_dense + s_off[it], s_cnt[it]);
 #endif
                 }
                 dec_worker_sync(team);
@@ -1437,7 +1438,7 @@ __global__ void __launch_bounds__(kDecTeams * kDecBlock, 1) decode_batch_kernel(
         const uint64_t tile_base = s_hand_prefix[(hand - 1) & 1];
         if (tid == 0 && tile > 0)
             st_relaxed_u64(&a.tile_state[tile], (kLbPrefix << kLbFlagShift) | ((tile_base + total) & kLbValueMask));
-        for (uint32_t it = tid; it < nitems; it += kDecThreads) b.out_offsets[item0 + it] = tile_base + s_off[par][it];
+        for (uint32_t it = tid; it < nitems; it += kDecThreads) b.out_offsets[item0 + it] = tile_base + s_off[it];
         if (tid == 0 && item0 + nitems == b.n) b.out_offsets[b.n] = tile_base + total;
         HB_PHASE_MARK(4);  // wait for the position
         if (staged) {
@@ -1449,7 +1450,7 @@ __global__ void __launch_bounds__(kDecTeams * kDecBlock, 1) decode_batch_kernel(
                 const uint32_t gslot = g * 32 + lane;
                 if (gslot < nitems) {
                     const uint32_t it = s_perm[gslot];
-                    const uint64_t off = tile_base + s_off[par][it];
+                    const uint64_t off = tile_base + s_off[it];
                     const uint64_t room = off < b.out_capacity ? b.out_capacity - off : 0;
                     const uint64_t in0 = kFramed ? byte0 + (s_start[it] >> 3) - lead : b.in_offsets[item0 + it];
                     const uint64_t len = kFramed ? (uint64_t)s_bytes[it] : b.in_offsets[item0 + it + 1] - in0;

@@ -151,7 +151,7 @@ struct aws_huffman_batch_ctx {
     bool force_generic = false, no_slots = false, no_strings = false, no_fused_stream = false, no_rows = false;
     int rows_blocks_per_sm = 0, compact_blocks_per_sm = 0;
     bool no_slots_decode = false;
-    size_t slots_static_smem = 0;
+    size_t slots_static_smem = 0, dec_static_smem[2] = {0, 0};
 };
 
 namespace {
@@ -487,8 +487,14 @@ int decode_batch_fast(
     // image (which reuses the stage and the front of the rows) must end before row offset `front`
     // (decode_batch_kernel step 4): rows <= stage + front - 32.
     const size_t lut_bytes = (size_t)a.lut2_count * 8;
-    // one block per SM: [LUT2][team 0: stage, rows][team 1: stage, rows] + the teams' static arrays
-    const size_t budget = ((size_t)224 * 1024 - lut_bytes) / kDecTeams - 9 * 1024 /* static */;
+    // one block per SM: [LUT2][team 0: stage, rows][team 1: stage, rows] + the teams' static arrays (what the kernel
+    // declares is asked from the runtime: every KB of the SM's 227 is a string more per tile)
+    if (!ctx->dec_static_smem[framed]) {
+        cudaFuncAttributes attr{};
+        HB_CUDA_TRY(framed ? cudaFuncGetAttributes(&attr, decode_batch_kernel<true>) : cudaFuncGetAttributes(&attr, decode_batch_kernel<false>));
+        ctx->dec_static_smem[framed] = attr.sharedSizeBytes;
+    }
+    const size_t budget = (((size_t)227 * 1024 - ctx->dec_static_smem[framed] - lut_bytes) / kDecTeams - 128) & ~size_t(15);
     const double expand = 8.0 / a.min_len;
     size_t stage_bytes = (size_t)((double)budget / (1.0 + expand)) & ~size_t(15);
     stage_bytes = std::max<size_t>(stage_bytes, 2 * kDecMaxRow);
@@ -497,15 +503,19 @@ int decode_batch_fast(
     rows_bytes = std::min(rows_bytes, stage_bytes + front - 64) & ~size_t(15);
     a.stage_words = (uint32_t)(stage_bytes / 4 - 2);
     a.rows_bytes = (uint32_t)rows_bytes;
-    // strings per tile: as many as fit the stage and the row area at the batch's average length, in whole warps,
-    // with 20 % to spare for tiles above the average (a tile that does not fit takes the two-pass global route
-    // and every tile behind it waits for its count: at 12 % two tiles in 4,500 overflowed on the benchmark)
+    // strings per tile: as many as fit the stage and the row area at the batch's average length, with room to spare
+    // for tiles above the average (a tile that does not fit takes the two-pass global route and every tile behind it
+    // waits for its count)
     {
         const double avg = std::max(1.0, (double)total_in / (double)v.n);
-        const double by_stage = (double)(stage_bytes - 64) / (1.2 * avg);
-        const double by_rows = (double)rows_bytes / (1.2 * avg * expand + kDecRowSlack);
+        // (17 % to spare: on the benchmark's uniform 8..256 B strings a tile's bytes vary by 3.2 % (one sigma); with 12 %
+        // two tiles in 4,500 overflowed, 20 % cost the ninth group of the tile)
+        const double by_stage = (double)(stage_bytes - 64) / (1.17 * avg);
+        const double by_rows = (double)rows_bytes / (1.17 * avg * expand + kDecRowSlack);
         const uint64_t fit = (uint64_t)std::max(32.0, std::min(by_stage, by_rows));
-        a.items_per_tile = (uint32_t)std::min<uint64_t>(kDecItemsPerTile, fit & ~uint64_t(31));
+        // (in steps of 8 strings: the last group of a tile may be partly empty — it holds the tile's shortest strings —
+        // and every string more per tile is decode-phase time shared by one more: 272 instead of 256 on the benchmark)
+        a.items_per_tile = (uint32_t)std::min<uint64_t>(kDecItemsPerTile, std::max<uint64_t>(32, fit & ~uint64_t(7)));
     }
     const uint64_t num_tiles = (v.n + a.items_per_tile - 1) / a.items_per_tile;
     const size_t state_bytes = num_tiles * sizeof(uint64_t) + 256;
