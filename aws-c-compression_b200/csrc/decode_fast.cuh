@@ -981,7 +981,10 @@ constexpr int kDecTeams = HB_DEC_TEAMS;      // teams per block (they share the 
 #endif
 constexpr int kDecPullWarps = HB_DEC_PULL_WARPS;
 constexpr uint32_t kDecDone = 0xffffffffu;
-constexpr int kDecItemsPerTile = 288;        // strings per tile (9 groups of 32)
+#ifndef HB_DEC_ITEMS_PER_TILE
+#define HB_DEC_ITEMS_PER_TILE 288
+#endif
+constexpr int kDecItemsPerTile = HB_DEC_ITEMS_PER_TILE;  // strings per tile at most (9 groups of 32)
 // Named barriers (as in encode_tiled.cuh). Workers among themselves: 1. Hand-off of a tile to the scout: 2 + parity
 // (workers arrive without waiting, the scout waits). Result of a look-back: 4 + parity (the scout arrives, the
 // workers wait).

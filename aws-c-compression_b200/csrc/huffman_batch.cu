@@ -199,7 +199,10 @@ int ensure_dynamic_smem(K kernel, int device, size_t bytes) {
     return AWS_OP_SUCCESS;
 }
 
-constexpr uint32_t kLutRootBits = 12;
+#ifndef HB_LUT_ROOT_BITS
+#define HB_LUT_ROOT_BITS 12
+#endif
+constexpr uint32_t kLutRootBits = HB_LUT_ROOT_BITS;
 constexpr uint32_t kLutSubBits = 8;
 constexpr uint32_t kLutMaxSmemEntries = 8192;  // 32 KiB
 
