@@ -50,7 +50,7 @@ namespace hb {
 #define HB_STR_PACK_BLOCKS 2
 #endif
 
-constexpr int kStrThreads = 256;
+constexpr int kStrThreads = 256;  // (the sort's 256 buckets and the scan's tiles are laid out for this)
 constexpr int kStrWarps = kStrThreads / 32;
 constexpr int kStrBatch = 2 * kStrThreads;                   // strings sorted and dealt out together
 constexpr uint32_t kStrTileBytes = HB_STR_TILE_BYTES;        // T: output bytes per tile (multiple of 16)
